@@ -1,0 +1,97 @@
+// sa_host.cu — error plumbing, TMA descriptor encoding (driver entry point fetched at run time so the library
+// has no link-time dependency on libcuda), and the library-level C-ABI queries.
+#include "sa_host.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/stableavatar_b200.h"
+
+namespace sa {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return SA_ERR_CUDA;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable (%s)", cudaGetErrorName(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return SA_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("TMA base pointer %p is not 16-byte aligned", base);
+    return SA_ERR_BAD_ARG;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i - 1];
+      if (gstr[i - 1] % 16 != 0) {
+        set_error("TMA stride %d = %llu bytes is not a multiple of 16", i, (unsigned long long)gstr[i - 1]);
+        return SA_ERR_BAD_ARG;
+      }
+    }
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
+              (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0), bx[0], rank > 1 ? bx[1] : 0);
+    return SA_ERR_CUDA;
+  }
+  return SA_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+}  // namespace sa
+
+extern "C" {
+
+int sa_version(void) { return 100; }
+
+const char* sa_last_error(void) { return sa::g_err; }
+
+int sa_device_sm_count(void) { return sa::sm_count(); }
+
+}  // extern "C"
