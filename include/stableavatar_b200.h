@@ -76,6 +76,86 @@ typedef struct {
 } sa_attn_args;
 int sa_flash_attn_d128(const sa_attn_args* args, sa_stream_t stream);
 
+/* Same contract for a handful of queries per (batch, head) and any head_dim % 8 == 0: the audio adapter's
+ * cross-attention, 15 audio tokens x 1560 video tokens x 8 heads of 192
+ * (wan/models/vocal_projector_fantasy_1B.py:259-277; SDPA branch :178-203). q_len <= 16,
+ * q_len * (head_dim + kv_len) * 4 <= 200 KB. accumulate must be 0. */
+int sa_attn_small_q(const sa_attn_args* args, int32_t head_dim, sa_stream_t stream);
+
+/* ---- LayerNorm (+affine) (+AdaLN modulation) (+gated self-residual) ------------------------------------------
+ * y = (x - mean) * rstd [* weight + bias]                     WanLayerNorm, 1B.py:345-355 (norm1/norm2/norm3/head.norm),
+ *                                                             nn.LayerNorm in MLPProj (:731-734) and VocalProjModel (vp1B:396-399)
+ * y = y * (1 + scale[b]) + shift[b]                           1B.py:675, 687, 721-722; vp1B.py:345, 354, 386
+ * out = res + y * gate[b]                                     vp1B.py:345-347 (adapter "pseudo self-attention")
+ * b = row / rows_per_batch; shift/scale/gate: bf16, batch stride mod_bs elements. round_bf16 = 1 replicates the bf16
+ * rounding after every elementwise op (bf16 residual stream under autocast); 0 keeps fp32 (adapter stream).
+ * x: x_dtype, out (and res): out_dtype, weight/bias: w_dtype. C % 8 == 0, C <= 2048.
+ */
+typedef struct {
+  const void* x;
+  void* out;
+  const void* weight;
+  const void* bias;
+  const void* shift;
+  const void* scale;
+  const void* gate;
+  const void* res;
+  int64_t ldx, ldo, ldr, mod_bs;
+  int32_t rows, C, rows_per_batch;
+  int32_t x_dtype, out_dtype, w_dtype, round_bf16;
+  float eps;
+} sa_ln_args;
+int sa_layernorm_modulate(const sa_ln_args* args, sa_stream_t stream);
+
+/* ---- RMSNorm over the full channel dim (+ 3-D RoPE), in place on bf16 ------------------------------------------
+ * x = bf16(bf16(x * rsqrt(mean(x^2) + eps)) * weight)          WanRMSNorm, 1B.py:326-342 (norm_q/norm_k/norm_k_img, vp1B norm_q/k)
+ * then, if freqs != NULL, token t = row % rows_per_batch < F*H*W is rotated pairwise by freqs[pos][j] (cos, sin),
+ * pos = frame / row / column index for j < 22 / < 43 / < 64       rope_apply, 1B.py:296-323; table 1B.py:855-862
+ * Up to two segments (q and k of a fused QKV GEMM output) share the launch: x/weight and x2/weight2 (x2 may be NULL).
+ * freqs: float [1024][64][2]. C % 8 == 0 (C % 128 == 0 with RoPE), ld % 8 == 0.
+ */
+typedef struct {
+  void* x;
+  const void* weight;
+  void* x2;
+  const void* weight2;
+  const void* freqs;
+  int64_t ld;
+  int32_t rows, C, rows_per_batch, F, H, W;
+  float eps;
+} sa_rms_args;
+int sa_rmsnorm_rope(const sa_rms_args* args, sa_stream_t stream);
+
+/* out[i, j, :] = bf16(a[i, :] + b[j, :]) (bf16): e = modulation + e0 of every block in one launch (1B.py:672). */
+int sa_add_bcast_bf16(const void* a, const void* b, void* out, int32_t na, int32_t nb, int32_t n, sa_stream_t stream);
+
+/* ---- patch embedding operand / output rearrangement ------------------------------------------------------------
+ * sa_patchify: A[b, tok, c*4 + q*2 + r] = cat(x, y)[b, c, f, 2h+q, 2w+r] (bf16), rows past F*H/2*W/2 and columns past
+ * 4*(Cx+Cy) zero — the K-major operand that turns patch_embedding (Conv3d k=s=(1,2,2), 1B.py:830-831, 972-983) into
+ * a GEMM against weight.flatten(1). sa_unpatchify: 1B.py:1161-1184 on the head output u[b, tok, (q*2+r)*Cout + c].
+ */
+int sa_patchify(const void* x, const void* y, void* out, int32_t B, int32_t Cx, int32_t Cy, int32_t F, int32_t H,
+                int32_t W, int32_t seq_len, int32_t K_pad, sa_stream_t stream);
+int sa_unpatchify(const void* u, void* out, int64_t u_bs, int64_t u_ls, int32_t B, int32_t Cout, int32_t F, int32_t H,
+                  int32_t W, sa_stream_t stream);
+
+/* out[m, n] = sum_k pre(x[m, k]) * W[n, k] + bias[n] in fp32 (M <= 8): the time-embedding island that the reference
+ * runs under autocast(dtype=float32) (1B.py:986-990). pre: 0 none, 1 SiLU, 2 x is t[M] and the input row is
+ * sinusoidal_embedding_1d(K, t) computed in fp64 (1B.py:210-220). Writes fp32 and/or bf16 copies. */
+int sa_small_linear_f32(const void* x, const void* w, const void* bias, void* out_f32, void* out_bf16, int32_t M,
+                        int32_t N, int32_t K, int32_t pre, int32_t w_dtype, sa_stream_t stream);
+
+/* out[r, :] = idx[r] >= 0 ? src[idx[r], :] : 0 (fp32 rows): split_tensor_with_padding, vocal_projector_fantasy.py:81-131. */
+int sa_gather_rows_f32(const void* src, const void* idx, void* out, int32_t rows, int32_t C, sa_stream_t stream);
+
+/* ---- scheduler step ------------------------------------------------------------------------------------------
+ * cfg != 0: pred = [uncond, drop_audio, cond] (3 x n bf16); noise = uncond + audio_scale*(drop_audio - uncond) +
+ * text_scale*(cond - drop_audio), each op rounded to bf16 (wan/pipeline/wan_inference_long_pipeline.py:751-753).
+ * out = bf16(float(latents) + dsigma * float(noise)): FlowMatchEulerDiscreteScheduler.step of diffusers 0.30.1
+ * (pipe.py:754). noise_out (optional) receives the combined prediction. */
+int sa_cfg_euler_step(const void* pred, const void* latents, void* out, void* noise_out, int64_t n, float audio_scale,
+                      float text_scale, float dsigma, int32_t cfg, sa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

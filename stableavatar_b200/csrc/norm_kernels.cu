@@ -1,0 +1,306 @@
+// norm_kernels.cu — HBM-bound row kernels of the DiT block: LayerNorm (+affine) (+AdaLN modulate) (+gated self
+// residual), RMSNorm (+3-D RoPE), and the modulation-table broadcast add.
+//
+// One warp owns one row: each lane keeps its 16-byte chunks of the row in registers (C/256 chunks, 6 for C = 1536),
+// statistics are reduced with shuffles, so a row is read once and written once (algorithmic bytes = 2 x row bytes),
+// there is no shared memory and no block barrier, and every load/store is a coalesced 128-bit access.
+//
+// Rounding points follow the reference's bf16 autocast flow:
+//   WanLayerNorm   (1B.py:345-355): stats in fp32, result .type_as(x)
+//   modulation     (1B.py:675-676): norm(x) * (1 + e1) + e0, every op rounded to bf16 when x is bf16
+//   WanRMSNorm     (1B.py:326-342): (x * rsqrt(mean(x^2) + eps)).type_as(x) * weight
+//   rope_apply     (1B.py:296-323): adjacent pairs rotated by exp(i * pos * theta_j), 22/21/21 pairs for (f, h, w)
+#include "../../include/stableavatar_b200.h"
+#include "sa_host.h"
+#include "sa_ptx.cuh"
+
+namespace sa {
+namespace norm {
+
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int MAX_CHUNKS = 8;  // C <= 8 * 256 = 2048 per warp-row
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void load_chunk(const void* base, int dtype, long long idx, float (&v)[8]) {
+  if (dtype == SA_BF16) {
+    uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+__device__ __forceinline__ void store_chunk(void* base, int dtype, long long idx, const float (&v)[8]) {
+  if (dtype == SA_BF16) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]);
+    u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]);
+    u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = u;
+  } else {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+struct LnParams {
+  const void* x; void* out;
+  const void* weight; const void* bias;
+  const __nv_bfloat16* shift; const __nv_bfloat16* scale; const __nv_bfloat16* gate;
+  const void* res;
+  long long ldx, ldo, ldr, mod_bs;
+  int rows, C, rows_per_batch, x_dtype, out_dtype, w_dtype, round_bf16;
+  float eps;
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) layernorm_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int nchunks = p.C >> 3;
+  float v[NCH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + c * 32;
+    if (ch < nchunks) {
+      load_chunk(p.x, p.x_dtype, (long long)row * p.ldx + ch * 8, v[c]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[c][i];
+    }
+  }
+  const float mean = warp_sum(s) / p.C;
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (lane + c * 32 < nchunks) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[c][i] - mean;
+        ss += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / p.C + p.eps);
+  const long long mrow = (long long)(row / p.rows_per_batch) * p.mod_bs;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + c * 32;
+    if (ch >= nchunks) continue;
+    const int col = ch * 8;
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = (v[c][i] - mean) * rstd;
+    if (p.weight) {
+      float w[8], b[8];
+      load_chunk(p.weight, p.w_dtype, col, w);
+      load_chunk(p.bias, p.w_dtype, col, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = fmaf(y[i], w[i], b[i]);
+    }
+    if (p.round_bf16) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = bf16_round(y[i]);
+    }
+    if (p.scale) {
+      float sc[8], sh[8];
+      load_chunk(p.scale, SA_BF16, mrow + col, sc);
+      load_chunk(p.shift, SA_BF16, mrow + col, sh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float one_plus = bf16_round(1.0f + sc[i]);  // (1 + e1) is a bf16 op in both streams
+        float t = y[i] * one_plus;
+        if (p.round_bf16) t = bf16_round(t);
+        t += sh[i];
+        if (p.round_bf16) t = bf16_round(t);
+        y[i] = t;
+      }
+    }
+    if (p.gate) {  // adapter "pseudo self-attention" (vp1B.py:345-347): out = res + y * e2
+      float g[8], r[8];
+      load_chunk(p.gate, SA_BF16, mrow + col, g);
+      load_chunk(p.res, p.out_dtype, (long long)row * p.ldr + col, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = r[i] + y[i] * g[i];
+    }
+    store_chunk(p.out, p.out_dtype, (long long)row * p.ldo + col, y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm + RoPE
+struct RmsParams {
+  __nv_bfloat16* x[2];
+  const __nv_bfloat16* weight[2];
+  const float2* freqs;  // [1024][64] (cos, sin), NULL = no rotation
+  long long ld;
+  int rows, C, rows_per_batch, F, H, W;
+  float eps;
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) rmsnorm_rope_kernel(const RmsParams p) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  __nv_bfloat16* x = p.x[blockIdx.y];
+  const __nv_bfloat16* wgt = p.weight[blockIdx.y];
+  const int nchunks = p.C >> 3;
+  float v[NCH][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + c * 32;
+    if (ch < nchunks) {
+      load_chunk(x, SA_BF16, (long long)row * p.ld + ch * 8, v[c]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += v[c][i] * v[c][i];
+    }
+  }
+  const float rinv = rsqrtf(warp_sum(ss) / p.C + p.eps);
+  const int tok = row % p.rows_per_batch;
+  const bool rotate = p.freqs != nullptr && tok < p.F * p.H * p.W;
+  const int pf = tok / (p.H * p.W), ph = (tok / p.W) % p.H, pw = tok % p.W;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + c * 32;
+    if (ch >= nchunks) continue;
+    const int col = ch * 8;
+    float w[8], y[8];
+    load_chunk(wgt, SA_BF16, col, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = bf16_round(bf16_round(v[c][i] * rinv) * w[i]);
+    if (rotate) {
+      const int j0 = (col & 127) >> 1;  // first complex pair of this chunk inside its head
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = j0 + i;
+        const int pos = j < 22 ? pf : (j < 43 ? ph : pw);
+        const float2 cs = __ldg(&p.freqs[pos * 64 + j]);
+        const float a = y[2 * i], b = y[2 * i + 1];
+        y[2 * i] = a * cs.x - b * cs.y;
+        y[2 * i + 1] = a * cs.y + b * cs.x;
+      }
+    }
+    store_chunk(x, SA_BF16, (long long)row * p.ld + col, y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ broadcast add
+// out[i, j, :] = bf16(a[i, :] + b[j, :])   — e = modulation + e0 for every block at once (1B.py:672)
+__global__ void add_bcast_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* out, int na, int nb,
+                                 int n) {
+  const long long total = (long long)na * nb * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int col = idx % n;
+    const long long r = idx / n;
+    const int j = r % nb, i = r / nb;
+    out[idx] = __float2bfloat16_rn(__bfloat162float(a[(long long)i * n + col]) + __bfloat162float(b[(long long)j * n + col]));
+  }
+}
+
+}  // namespace norm
+}  // namespace sa
+
+extern "C" int sa_layernorm_modulate(const sa_ln_args* a, sa_stream_t stream_) {
+  using namespace sa;
+  using namespace sa::norm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->x || !a->out) { set_error("sa_layernorm_modulate: null pointer"); return SA_ERR_BAD_ARG; }
+  if (a->rows <= 0) return SA_OK;
+  if (a->C <= 0 || a->C % 8 || a->C > MAX_CHUNKS * 256 || a->ldx % 8 || a->ldo % 8) {
+    set_error("sa_layernorm_modulate: C must be a multiple of 8 and <= %d, strides multiples of 8 (C=%d)",
+              MAX_CHUNKS * 256, a->C);
+    return SA_ERR_BAD_ARG;
+  }
+  if ((a->weight == nullptr) != (a->bias == nullptr) || (a->shift == nullptr) != (a->scale == nullptr) ||
+      (a->gate && !a->res)) {
+    set_error("sa_layernorm_modulate: weight/bias, shift/scale must come in pairs; gate needs res");
+    return SA_ERR_BAD_ARG;
+  }
+  LnParams p;
+  p.x = a->x; p.out = a->out; p.weight = a->weight; p.bias = a->bias;
+  p.shift = reinterpret_cast<const __nv_bfloat16*>(a->shift);
+  p.scale = reinterpret_cast<const __nv_bfloat16*>(a->scale);
+  p.gate = reinterpret_cast<const __nv_bfloat16*>(a->gate);
+  p.res = a->res;
+  p.ldx = a->ldx; p.ldo = a->ldo; p.ldr = a->ldr; p.mod_bs = a->mod_bs;
+  p.rows = a->rows; p.C = a->C; p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : a->rows;
+  p.x_dtype = a->x_dtype; p.out_dtype = a->out_dtype; p.w_dtype = a->w_dtype; p.round_bf16 = a->round_bf16;
+  p.eps = a->eps;
+  const int grid = (a->rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  const int nch = (a->C / 8 + 31) / 32;
+  if (nch <= 2) layernorm_kernel<2><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  else if (nch <= 6) layernorm_kernel<6><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  else layernorm_kernel<8><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "layernorm_kernel launch");
+  return SA_OK;
+}
+
+extern "C" int sa_rmsnorm_rope(const sa_rms_args* a, sa_stream_t stream_) {
+  using namespace sa;
+  using namespace sa::norm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->x || !a->weight) { set_error("sa_rmsnorm_rope: null pointer"); return SA_ERR_BAD_ARG; }
+  if (a->rows <= 0) return SA_OK;
+  if (a->C <= 0 || a->C % 8 || a->C > MAX_CHUNKS * 256 || a->ld % 8) {
+    set_error("sa_rmsnorm_rope: C must be a multiple of 8 and <= %d (C=%d)", MAX_CHUNKS * 256, a->C);
+    return SA_ERR_BAD_ARG;
+  }
+  if (a->freqs && (a->C % 128 || a->F > 1024 || a->H > 1024 || a->W > 1024 || a->F <= 0 || a->H <= 0 || a->W <= 0)) {
+    set_error("sa_rmsnorm_rope: RoPE needs head_dim 128 and 0 < F,H,W <= 1024");
+    return SA_ERR_BAD_ARG;
+  }
+  if ((a->x2 == nullptr) != (a->weight2 == nullptr)) { set_error("sa_rmsnorm_rope: x2/weight2 pair"); return SA_ERR_BAD_ARG; }
+  RmsParams p;
+  p.x[0] = reinterpret_cast<__nv_bfloat16*>(a->x);
+  p.x[1] = reinterpret_cast<__nv_bfloat16*>(a->x2);
+  p.weight[0] = reinterpret_cast<const __nv_bfloat16*>(a->weight);
+  p.weight[1] = reinterpret_cast<const __nv_bfloat16*>(a->weight2);
+  p.freqs = reinterpret_cast<const float2*>(a->freqs);
+  p.ld = a->ld; p.rows = a->rows; p.C = a->C;
+  p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : a->rows;
+  p.F = a->F; p.H = a->H; p.W = a->W; p.eps = a->eps;
+  dim3 grid((a->rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, a->x2 ? 2 : 1);
+  const int nch = (a->C / 8 + 31) / 32;
+  if (nch <= 2) rmsnorm_rope_kernel<2><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  else if (nch <= 6) rmsnorm_rope_kernel<6><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  else rmsnorm_rope_kernel<8><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "rmsnorm_rope_kernel launch");
+  return SA_OK;
+}
+
+extern "C" int sa_add_bcast_bf16(const void* a, const void* b, void* out, int32_t na, int32_t nb, int32_t n,
+                                 sa_stream_t stream_) {
+  using namespace sa;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !b || !out || na <= 0 || nb <= 0 || n <= 0) { set_error("sa_add_bcast_bf16: bad argument"); return SA_ERR_BAD_ARG; }
+  const long long total = (long long)na * nb * n;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  norm::add_bcast_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+                                                   reinterpret_cast<const __nv_bfloat16*>(b),
+                                                   reinterpret_cast<__nv_bfloat16*>(out), na, nb, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "add_bcast_kernel launch");
+  return SA_OK;
+}

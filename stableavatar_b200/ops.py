@@ -1,0 +1,195 @@
+"""Host-side wrappers over the C-ABI (include/stableavatar_b200.h). torch tensors are used as device memory only:
+each wrapper fills the argument struct from pointers/strides and launches on the current CUDA stream. There is no
+eager fallback — a missing library or a CPU tensor raises."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_SILU  # noqa: F401
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("stableavatar_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def gemm(a, w, bias=None, *, out=None, act=ACT_NONE, res=None, gate=None, gate_ld=0, rows_per_batch=0, round_y=True,
+         out_dtype=torch.bfloat16):
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) — see sa_gemm_bf16. a may be a row-strided 2-D view."""
+    _need_cuda(a, w)
+    assert a.dim() == 2 and w.dim() == 2 and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (a.shape, w.shape)
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    g = L.GemmArgs(a=a.data_ptr(), w=w.data_ptr(), out=out.data_ptr(), bias=L.ptr(bias), res=L.ptr(res),
+                   gate=L.ptr(gate), lda=a.stride(0), ldw=w.stride(0), ldc=out.stride(0),
+                   ldr=res.stride(0) if res is not None else 0, gate_ld=gate_ld, M=M, N=N, K=K,
+                   bias_dtype=L.dt(bias) if bias is not None else 0, out_dtype=L.dt(out),
+                   res_dtype=L.dt(res) if res is not None else 0, act=act,
+                   res_mode=0 if res is None else (2 if gate is not None else 1), round_y=int(round_y),
+                   rows_per_batch=rows_per_batch)
+    L.check(L.lib().sa_gemm_bf16(C.byref(g), L.stream_ptr()), "sa_gemm_bf16")
+    return out
+
+
+def _attn_args(q, k, v, out, accumulate, scale):
+    B, Lq, H, D = q.shape
+    assert k.shape[0] == B and k.shape[2] == H and k.shape[3] == D and v.shape == k.shape
+    for t in (q, k, v, out):
+        assert t.dtype == torch.bfloat16 and t.stride(3) == 1 and t.stride(2) == D
+    return L.AttnArgs(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), out=out.data_ptr(), q_bs=q.stride(0),
+                      q_ls=q.stride(1), k_bs=k.stride(0), k_ls=k.stride(1), v_bs=v.stride(0), v_ls=v.stride(1),
+                      o_bs=out.stride(0), o_ls=out.stride(1), batch=B, heads=H, q_len=Lq, kv_len=k.shape[1],
+                      scale=scale if scale is not None else D ** -0.5, accumulate=int(accumulate))
+
+
+def flash_attn(q, k, v, out=None, accumulate=False, scale=None):
+    """softmax(q k^T * scale) v for [B, L, H, 128] bf16 views (token/batch strides free) — sa_flash_attn_d128."""
+    _need_cuda(q, k, v)
+    if q.shape[3] != 128:
+        raise NotImplementedError("flash_attn: head_dim 128 only")
+    if out is None:
+        assert not accumulate
+        out = torch.empty(q.shape, device=q.device, dtype=torch.bfloat16)
+    g = _attn_args(q, k, v, out, accumulate, scale)
+    L.check(L.lib().sa_flash_attn_d128(C.byref(g), L.stream_ptr()), "sa_flash_attn_d128")
+    return out
+
+
+def attn_small_q(q, k, v, out=None, scale=None):
+    """Few-queries attention (audio adapter), any head_dim % 8 == 0 — sa_attn_small_q."""
+    _need_cuda(q, k, v)
+    if out is None:
+        out = torch.empty(q.shape, device=q.device, dtype=torch.bfloat16)
+    g = _attn_args(q, k, v, out, False, scale)
+    L.check(L.lib().sa_attn_small_q(C.byref(g), C.c_int32(q.shape[3]), L.stream_ptr()), "sa_attn_small_q")
+    return out
+
+
+class LnArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p),
+                ("shift", C.c_void_p), ("scale", C.c_void_p), ("gate", C.c_void_p), ("res", C.c_void_p),
+                ("ldx", C.c_int64), ("ldo", C.c_int64), ("ldr", C.c_int64), ("mod_bs", C.c_int64),
+                ("rows", C.c_int32), ("C", C.c_int32), ("rows_per_batch", C.c_int32),
+                ("x_dtype", C.c_int32), ("out_dtype", C.c_int32), ("w_dtype", C.c_int32), ("round_bf16", C.c_int32),
+                ("eps", C.c_float)]
+
+
+def layernorm(x, *, weight=None, bias=None, shift=None, scale=None, gate=None, res=None, mod_bs=0, rows_per_batch=0,
+              eps=1e-6, out=None, out_dtype=torch.bfloat16, round_bf16=True):
+    """LayerNorm (+affine) (+modulate) (+gated residual) over the last dim of a 2-D row view — sa_layernorm_modulate."""
+    _need_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, Cc = x.shape
+    if out is None:
+        out = torch.empty(rows, Cc, device=x.device, dtype=out_dtype)
+    for t in (shift, scale, gate):
+        assert t is None or t.dtype == torch.bfloat16
+    if res is not None:
+        assert res.dtype == out.dtype
+    a = LnArgs(x=x.data_ptr(), out=out.data_ptr(), weight=L.ptr(weight), bias=L.ptr(bias), shift=L.ptr(shift),
+               scale=L.ptr(scale), gate=L.ptr(gate), res=L.ptr(res), ldx=x.stride(0), ldo=out.stride(0),
+               ldr=res.stride(0) if res is not None else 0, mod_bs=mod_bs, rows=rows, C=Cc,
+               rows_per_batch=rows_per_batch, x_dtype=L.dt(x), out_dtype=L.dt(out),
+               w_dtype=L.dt(weight) if weight is not None else 0, round_bf16=int(round_bf16), eps=eps)
+    L.check(L.lib().sa_layernorm_modulate(C.byref(a), L.stream_ptr()), "sa_layernorm_modulate")
+    return out
+
+
+class RmsArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("weight", C.c_void_p), ("x2", C.c_void_p), ("weight2", C.c_void_p),
+                ("freqs", C.c_void_p), ("ld", C.c_int64), ("rows", C.c_int32), ("C", C.c_int32),
+                ("rows_per_batch", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("eps", C.c_float)]
+
+
+def rmsnorm_rope_(x, weight, x2=None, weight2=None, freqs=None, grid=(1, 1, 1), rows_per_batch=0, eps=1e-6):
+    """In-place RMSNorm (+RoPE) on one or two bf16 row views sharing a row stride — sa_rmsnorm_rope."""
+    _need_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
+    if x2 is not None:
+        assert x2.shape == x.shape and x2.stride() == x.stride() and weight2.dtype == torch.bfloat16
+    if freqs is not None:
+        assert freqs.dtype == torch.float32 and freqs.shape == (1024, 64, 2) and freqs.is_contiguous()
+    a = RmsArgs(x=x.data_ptr(), weight=weight.data_ptr(), x2=L.ptr(x2), weight2=L.ptr(weight2), freqs=L.ptr(freqs),
+                ld=x.stride(0), rows=x.shape[0], C=x.shape[1], rows_per_batch=rows_per_batch, F=grid[0], H=grid[1],
+                W=grid[2], eps=eps)
+    L.check(L.lib().sa_rmsnorm_rope(C.byref(a), L.stream_ptr()), "sa_rmsnorm_rope")
+    return x
+
+
+def add_bcast(a, b):
+    """out[i, j, :] = bf16(a[i, :] + b[j, :])."""
+    _need_cuda(a, b)
+    assert a.dtype == b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous() and a.shape[1] == b.shape[1]
+    out = torch.empty(a.shape[0], b.shape[0], a.shape[1], device=a.device, dtype=torch.bfloat16)
+    L.check(L.lib().sa_add_bcast_bf16(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()),
+                                      a.shape[0], b.shape[0], a.shape[1], L.stream_ptr()), "sa_add_bcast_bf16")
+    return out
+
+
+def patchify(x, y, seq_len):
+    _need_cuda(x)
+    B, Cx, F, H, W = x.shape
+    Cy = y.shape[1] if y is not None else 0
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and (y is None or (y.dtype == torch.bfloat16 and y.is_contiguous()))
+    K = (Cx + Cy) * 4
+    K_pad = (K + 7) // 8 * 8
+    out = torch.empty(B, seq_len, K_pad, device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().sa_patchify(C.c_void_p(x.data_ptr()), C.c_void_p(L.ptr(y)), C.c_void_p(out.data_ptr()), B, Cx, Cy,
+                                F, H, W, seq_len, K_pad, L.stream_ptr()), "sa_patchify")
+    return out
+
+
+def unpatchify(u, B, Cout, F, H, W):
+    _need_cuda(u)
+    assert u.dim() == 3 and u.dtype == torch.bfloat16 and u.stride(2) == 1
+    out = torch.empty(B, Cout, F, H, W, device=u.device, dtype=torch.bfloat16)
+    L.check(L.lib().sa_unpatchify(C.c_void_p(u.data_ptr()), C.c_void_p(out.data_ptr()), C.c_int64(u.stride(0)),
+                                  C.c_int64(u.stride(1)), B, Cout, F, H, W, L.stream_ptr()), "sa_unpatchify")
+    return out
+
+
+def small_linear(x, w, bias, pre=0, want_f32=True, want_bf16=False, K=None):
+    """fp32 rows: out = pre(x) @ w^T + bias (M <= 8) — sa_small_linear_f32. pre=2: x is t[M], K = sinusoid width."""
+    _need_cuda(x, w)
+    assert x.dtype == torch.float32 and x.is_contiguous() and w.is_contiguous()
+    M = x.shape[0]
+    N, Kw = w.shape
+    of = torch.empty(M, N, device=x.device, dtype=torch.float32) if want_f32 else None
+    ob = torch.empty(M, N, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    L.check(L.lib().sa_small_linear_f32(C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(L.ptr(bias)),
+                                        C.c_void_p(L.ptr(of)), C.c_void_p(L.ptr(ob)), M, N, Kw, pre, L.dt(w),
+                                        L.stream_ptr()), "sa_small_linear_f32")
+    return of, ob
+
+
+def gather_rows(src, idx):
+    _need_cuda(src, idx)
+    assert src.dtype == torch.float32 and src.is_contiguous() and idx.dtype == torch.int32
+    out = torch.empty(idx.numel(), src.shape[1], device=src.device, dtype=torch.float32)
+    L.check(L.lib().sa_gather_rows_f32(C.c_void_p(src.data_ptr()), C.c_void_p(idx.data_ptr()), C.c_void_p(out.data_ptr()),
+                                       idx.numel(), src.shape[1], L.stream_ptr()), "sa_gather_rows_f32")
+    return out
+
+
+def cfg_euler_step(pred, latents, dsigma, audio_scale=0.0, text_scale=0.0, cfg=True, out=None, noise_out=None):
+    """latents' = bf16(float(latents) + dsigma * CFG(pred)) — sa_cfg_euler_step."""
+    _need_cuda(pred, latents)
+    assert pred.dtype == latents.dtype == torch.bfloat16 and pred.is_contiguous() and latents.is_contiguous()
+    n = latents.numel()
+    assert pred.numel() == (3 * n if cfg else n)
+    if out is None:
+        out = torch.empty_like(latents)
+    L.check(L.lib().sa_cfg_euler_step(C.c_void_p(pred.data_ptr()), C.c_void_p(latents.data_ptr()),
+                                      C.c_void_p(out.data_ptr()), C.c_void_p(L.ptr(noise_out)), C.c_int64(n),
+                                      C.c_float(audio_scale), C.c_float(text_scale), C.c_float(dsigma), int(cfg),
+                                      L.stream_ptr()), "sa_cfg_euler_step")
+    return out

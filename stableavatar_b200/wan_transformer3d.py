@@ -1,0 +1,421 @@
+"""StableAvatar's audio-conditioned Wan2.1 DiT on hand-written sm_100a kernels.
+
+Drop-in for `WanTransformer3DFantasyModel` of wan/models/wan_fantasy_transformer3d_1B.py (class at :741, forward at
+:928-1159): same constructor arguments, the same state-dict key names (so `load_state_dict` of a reference checkpoint
+works unchanged), the same `forward(x, t, context, seq_len, clip_fea, y, cond_flag, vocal_embeddings,
+is_clip_level_modeling, video_sample_n_frames)` signature and error behaviour, `.config`, `.freqs`,
+`enable_teacache / disable_teacache / enable_riflex / disable_riflex / enable_multi_gpus_inference`.
+
+The modules below only hold parameters; all arithmetic goes through the C-ABI library (stableavatar_b200.ops) and
+follows the reference's bf16 autocast rounding points. bf16 parameters on a CUDA device are
+required; there is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .vocal_projector import FantasyTalkingVocalCondition1BModel, _Linear, _Norm, _param
+
+
+def rope_params(max_seq_len, dim, theta=10000):
+    """1B.py:224-231 (complex128 table)."""
+    freqs = torch.outer(torch.arange(max_seq_len),
+                        1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float64).div(dim)))
+    return torch.polar(torch.ones_like(freqs), freqs)
+
+
+def rope_params_riflex(max_seq_len, dim, theta=10000.0, k=None, L_test=None, L_test_scale=None):
+    """1B.py:236-291 (get_1d_rotary_pos_embed_riflex, use_real=False)."""
+    freqs = 1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float64).div(dim))
+    if k is not None:
+        freqs[k - 1] = 0.9 * 2 * torch.pi / L_test
+    if L_test_scale is not None:
+        freqs[k - 1] = freqs[k - 1] / L_test_scale
+    freqs = torch.outer(torch.arange(max_seq_len), freqs)
+    return torch.polar(torch.ones_like(freqs), freqs)
+
+
+class TeaCache:
+    """wan/models/cache_utils.py:19-74 — state of the timestep-embedding-aware block-skipping cache."""
+
+    def __init__(self, coefficients, num_steps, rel_l1_thresh=0.0, num_skip_start_steps=0, offload=True):
+        if num_steps < 1:
+            raise ValueError(f"`num_steps` must be greater than 0 but is {num_steps}.")
+        if rel_l1_thresh < 0:
+            raise ValueError(f"`rel_l1_thresh` must be greater than or equal to 0 but is {rel_l1_thresh}.")
+        if num_skip_start_steps < 0 or num_skip_start_steps > num_steps:
+            raise ValueError("`num_skip_start_steps` must be great than or equal to 0 and "
+                             f"less than or equal to `num_steps={num_steps}` but is {num_skip_start_steps}.")
+        self.coefficients, self.num_steps, self.rel_l1_thresh = coefficients, num_steps, rel_l1_thresh
+        self.num_skip_start_steps, self.offload = num_skip_start_steps, offload
+        self.rescale_func = np.poly1d(coefficients)
+        self.reset()
+
+    @staticmethod
+    def compute_rel_l1_distance(prev, cur):
+        return ((cur.float() - prev.float()).abs().mean() / prev.float().abs().mean()).cpu().item()
+
+    def reset(self):
+        self.cnt, self.should_calc, self.accumulated_rel_l1_distance = 0, True, 0
+        self.previous_modulated_input = None
+        self.previous_residual = self.previous_residual_cond = self.previous_residual_uncond = None
+
+
+class WanSelfAttention(nn.Module):
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.dim, self.num_heads, self.head_dim = dim, num_heads, dim // num_heads
+        self.q, self.k, self.v, self.o = (_Linear(dim, dim) for _ in range(4))
+        self.norm_q, self.norm_k = _Norm(dim, bias=False), _Norm(dim, bias=False)
+
+
+class WanI2VTalkingCrossAttention(WanSelfAttention):
+    def __init__(self, dim, num_heads):
+        super().__init__(dim, num_heads)
+        self.k_img, self.v_img = _Linear(dim, dim), _Linear(dim, dim)
+        self.norm_k_img = _Norm(dim, bias=False)
+        self.k_vocal, self.v_vocal = _Linear(dim, dim), _Linear(dim, dim)
+
+
+class WanAttentionBlock(nn.Module):
+    def __init__(self, dim, ffn_dim, num_heads):
+        super().__init__()
+        self.self_attn = WanSelfAttention(dim, num_heads)
+        self.norm3 = _Norm(dim)
+        self.cross_attn = WanI2VTalkingCrossAttention(dim, num_heads)
+        self.ffn = nn.Sequential(_Linear(dim, ffn_dim), nn.Identity(), _Linear(ffn_dim, dim))
+        self.modulation = _param(1, 6, dim)
+
+
+class Head(nn.Module):
+    def __init__(self, dim, out_dim, patch_size):
+        super().__init__()
+        self.head = _Linear(dim, math.prod(patch_size) * out_dim)
+        self.modulation = _param(1, 2, dim)
+
+
+class MLPProj(nn.Module):
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.proj = nn.Sequential(_Norm(in_dim), _Linear(in_dim, in_dim), nn.Identity(), _Linear(in_dim, out_dim),
+                                  _Norm(out_dim))
+
+
+class _Conv3dParams(nn.Module):
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.weight = _param(cout, cin, *k)
+        self.bias = _param(cout)
+
+
+class WanTransformer3DFantasyModel(nn.Module):
+    def __init__(self, model_type="t2v", patch_size=(1, 2, 2), text_len=512, in_dim=16, dim=2048, ffn_dim=8192,
+                 freq_dim=256, text_dim=4096, out_dim=16, num_heads=16, num_layers=32, window_size=(-1, -1),
+                 qk_norm=True, cross_attn_norm=True, eps=1e-6, in_channels=16, hidden_size=2048):
+        super().__init__()
+        assert model_type in ["t2v", "i2v"]
+        if not (qk_norm and cross_attn_norm) or tuple(patch_size) != (1, 2, 2) or dim // num_heads != 128:
+            raise NotImplementedError("B200 path implements the shipped configuration: qk_norm, cross_attn_norm, "
+                                      "patch (1,2,2), head_dim 128")
+        cfg = dict(model_type=model_type, patch_size=tuple(patch_size), text_len=text_len, in_dim=in_dim, dim=dim,
+                   ffn_dim=ffn_dim, freq_dim=freq_dim, text_dim=text_dim, out_dim=out_dim, num_heads=num_heads,
+                   num_layers=num_layers, window_size=window_size, qk_norm=qk_norm, cross_attn_norm=cross_attn_norm,
+                   eps=eps, in_channels=in_channels, hidden_size=hidden_size)
+        self.config = SimpleNamespace(**cfg)
+        for k, v in cfg.items():
+            setattr(self, k, v)
+        self.patch_embedding = _Conv3dParams(in_dim, dim, patch_size)
+        self.text_embedding = nn.Sequential(_Linear(text_dim, dim), nn.Identity(), _Linear(dim, dim))
+        self.time_embedding = nn.Sequential(_Linear(freq_dim, dim), nn.Identity(), _Linear(dim, dim))
+        self.time_projection = nn.Sequential(nn.Identity(), _Linear(dim, dim * 6))
+        self.blocks = nn.ModuleList([WanAttentionBlock(dim, ffn_dim, num_heads) for _ in range(num_layers)])
+        self.head = Head(dim, out_dim, patch_size)
+        self.d = dim // num_heads
+        self.disable_riflex()
+        if model_type == "i2v":
+            self.img_emb = MLPProj(1280, dim)
+        self.teacache = None
+        self.sp_world_size, self.sp_world_rank, self.sp_group = 1, 0, None
+        self.vocal_projector = FantasyTalkingVocalCondition1BModel(audio_in_dim=768, audio_proj_dim=1536, dit_dim=dim)
+        self._prep = None
+        self.hooks = None          # test instrumentation: dict collecting per-block outputs when set
+
+    # ------------------------------------------------------------------ reference API surface
+    @property
+    def dtype(self):
+        return self.patch_embedding.weight.dtype
+
+    @property
+    def device(self):
+        return self.patch_embedding.weight.device
+
+    def enable_teacache(self, coefficients, num_steps, rel_l1_thresh, num_skip_start_steps=0, offload=True):
+        self.teacache = TeaCache(coefficients, num_steps, rel_l1_thresh=rel_l1_thresh,
+                                 num_skip_start_steps=num_skip_start_steps, offload=offload)
+
+    def disable_teacache(self):
+        self.teacache = None
+
+    def enable_riflex(self, k=6, L_test=66, L_test_scale=4.886):
+        d = self.d
+        self.freqs = torch.cat([rope_params_riflex(1024, d - 4 * (d // 6), k=k, L_test=L_test, L_test_scale=L_test_scale),
+                                rope_params(1024, 2 * (d // 6)), rope_params(1024, 2 * (d // 6))], dim=1)
+        self._freqs_dev = None
+
+    def disable_riflex(self):
+        d = self.d
+        self.freqs = torch.cat([rope_params(1024, d - 4 * (d // 6)), rope_params(1024, 2 * (d // 6)),
+                                rope_params(1024, 2 * (d // 6))], dim=1)
+        self._freqs_dev = None
+
+    def enable_multi_gpus_inference(self, group=None):
+        """1B.py:918-923. Sequence parallelism over `group` (default: the whole torch.distributed world)."""
+        import torch.distributed as dist
+        from . import sequence_parallel as sp
+        self.sp_group = group
+        self.sp_world_size = dist.get_world_size(group)
+        self.sp_world_rank = dist.get_rank(group)
+        self._sp = sp.plan(self.num_heads, self.sp_world_size, self.sp_world_rank)
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        self._prep = None
+        self.vocal_projector._prep = None
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
+
+    def _apply(self, fn, *a, **k):
+        self._prep = None
+        self.vocal_projector._prep = None
+        return super()._apply(fn, *a, **k)
+
+    # ------------------------------------------------------------------ one-time operand preparation
+    def _prepare(self):
+        if self._prep is not None:
+            return self._prep
+        w = self.patch_embedding.weight
+        if w.dtype != torch.bfloat16 or not w.is_cuda:
+            raise RuntimeError("WanTransformer3DFantasyModel (B200): parameters must be bf16 on a CUDA device "
+                               "(model.to('cuda', torch.bfloat16)); there is no CPU / fp32 fallback path")
+        cat = lambda *ts: torch.cat(ts).contiguous()  # noqa: E731
+        blocks = []
+        for b in self.blocks:
+            sa, ca = b.self_attn, b.cross_attn
+            blocks.append(dict(
+                w_qkv=cat(sa.q.weight, sa.k.weight, sa.v.weight), b_qkv=cat(sa.q.bias, sa.k.bias, sa.v.bias),
+                w_kv=cat(ca.k.weight, ca.v.weight), b_kv=cat(ca.k.bias, ca.v.bias),
+                w_kv_img=cat(ca.k_img.weight, ca.v_img.weight), b_kv_img=cat(ca.k_img.bias, ca.v_img.bias),
+                w_kv_voc=cat(ca.k_vocal.weight, ca.v_vocal.weight), b_kv_voc=cat(ca.k_vocal.bias, ca.v_vocal.bias)))
+        K = self.in_dim * 4
+        K_pad = (K + 7) // 8 * 8
+        w_pe = torch.zeros(self.dim, K_pad, device=w.device, dtype=w.dtype)
+        w_pe[:, :K] = w.reshape(self.dim, K)
+        self._prep = dict(blocks=blocks, w_pe=w_pe,
+                          mods=torch.stack([b.modulation.reshape(-1) for b in self.blocks]).contiguous(),
+                          head_mod=self.head.modulation.reshape(2, -1).contiguous())
+        return self._prep
+
+    def _freqs_table(self, device):
+        if self._freqs_dev is None or self._freqs_dev.device != device:
+            f = self.freqs[:, :64]
+            self._freqs_dev = torch.stack([f.real, f.imag], dim=-1).to(torch.float32).contiguous().to(device)
+        return self._freqs_dev
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x, t, context, seq_len, clip_fea=None, y=None, cond_flag=True, vocal_embeddings=None,
+                is_clip_level_modeling=False, video_sample_n_frames=81):
+        if self.model_type == "i2v":
+            assert clip_fea is not None and y is not None
+        p = self._prepare()
+        dev, bf = self.device, torch.bfloat16
+        C, nh = self.dim, self.num_heads
+        if isinstance(x, (list, tuple)):
+            x = torch.stack(list(x))
+        if isinstance(y, (list, tuple)):
+            y = torch.stack(list(y))
+        B, _, F, H, W = x.shape
+        Hp, Wp = H // 2, W // 2
+        Lv = F * Hp * Wp
+        P = self.sp_world_size
+        if P > 1:
+            seq_len = int(math.ceil(seq_len / P)) * P
+        assert Lv <= seq_len
+        L = seq_len
+
+        # patch embedding as a K = 4*in_dim GEMM; zero rows beyond the real tokens (1B.py:976-983)
+        A = ops.patchify(x.to(bf).contiguous(), None if y is None else y.to(bf).contiguous(), L)
+        h = ops.gemm(A.view(B * L, -1), p["w_pe"], self.patch_embedding.bias)
+        if L > Lv:
+            h.view(B, L, C)[:, Lv:].zero_()
+
+        # time embedding, fp32 island (1B.py:986-990)
+        te, tp = self.time_embedding, self.time_projection[1]
+        t32 = t.to(device=dev, dtype=torch.float32).contiguous()
+        h1, _ = ops.small_linear(t32, te[0].weight, te[0].bias, pre=2)
+        e32, e_bf = ops.small_linear(h1, te[2].weight, te[2].bias, pre=1, want_bf16=True)
+        _, e0 = ops.small_linear(e32, tp.weight, tp.bias, pre=1, want_f32=False, want_bf16=True)   # [B, 6C] bf16
+
+        # text / CLIP context (1B.py:994-1002)
+        ctx_in = torch.zeros(B, self.text_len, self.text_dim, device=dev, dtype=bf)
+        for i, u in enumerate(context):
+            ctx_in[i, :u.size(0)] = u
+        txe = self.text_embedding
+        ctx_txt = ops.gemm(ops.gemm(ctx_in.view(B * self.text_len, -1), txe[0].weight, txe[0].bias, act=ops.ACT_GELU_TANH),
+                           txe[2].weight, txe[2].bias)
+        ip = self.img_emb.proj
+        n_img = clip_fea.shape[1]
+        c = ops.layernorm(clip_fea.to(bf).reshape(B * n_img, -1).contiguous(), weight=ip[0].weight, bias=ip[0].bias, eps=1e-5)
+        c = ops.gemm(ops.gemm(c, ip[1].weight, ip[1].bias, act=ops.ACT_GELU_ERF), ip[3].weight, ip[3].bias)
+        ctx_img = ops.layernorm(c, weight=ip[4].weight, bias=ip[4].bias, eps=1e-5)
+        if n_img != 257:
+            raise RuntimeError("cross-attention expects 257 CLIP tokens (context[:, :257], 1B.py:544)")
+
+        # audio adapter (1B.py:1004-1009): once on the last sample for a CFG batch, replicated [0, vc, vc]
+        h3 = h.view(B, L, C)
+        e0_3 = e0.view(B, 6, C)
+        vocal_embeddings = vocal_embeddings.to(dev)
+        if vocal_embeddings.size(0) > 1:
+            vc, _ = self.vocal_projector(vocal_embeddings=vocal_embeddings[-1:], video_sample_n_frames=video_sample_n_frames,
+                                         latents=h3[-1:], e0=e0_3[-1:], e=e_bf[-1:])
+            vc = torch.cat([torch.zeros_like(vc), vc, vc])
+        else:
+            vc, _ = self.vocal_projector(vocal_embeddings=vocal_embeddings, video_sample_n_frames=video_sample_n_frames,
+                                         latents=h3, e0=e0_3, e=e_bf)
+        G = (video_sample_n_frames - 1) // 4 + 1
+        if vc.shape[0] != B:
+            raise RuntimeError(f"audio context batch {vc.shape[0]} != latent batch {B}")
+        if is_clip_level_modeling:
+            vc = vc.flatten(1, 2)
+        if self.hooks is not None:
+            self.hooks["vocal_context"] = vc
+            self.hooks["e0"] = e0_3
+
+        e_all = ops.add_bcast(p["mods"], e0)                                       # [layers, B, 6C]
+        freqs = self._freqs_table(dev)
+        state = dict(B=B, L=L, C=C, nh=nh, G=G, grid=(F, Hp, Wp), freqs=freqs, ctx_txt=ctx_txt, ctx_img=ctx_img,
+                     vc=vc.reshape(B, -1, C).contiguous(), vc_grouped=vc.dim() == 4)
+
+        if P > 1:
+            from . import sequence_parallel as sp
+            h, state = sp.shard_tokens(self, h, state)
+
+        def run_blocks(h):
+            for i in range(self.num_layers):
+                h = self._block(i, h, e_all[i], state)
+                if self.hooks is not None:
+                    self.hooks[f"block{i}"] = h.view(B, -1, C).clone()
+            return h
+
+        tc = self.teacache
+        if tc is not None:
+            if cond_flag:                                                          # 1B.py:1021-1046
+                skip_flag = tc.cnt < tc.num_skip_start_steps
+                if tc.cnt == 0 or tc.cnt == tc.num_steps - 1 or skip_flag:
+                    should_calc, tc.accumulated_rel_l1_distance = True, 0
+                else:
+                    rel = tc.compute_rel_l1_distance(tc.previous_modulated_input, e0_3)
+                    tc.accumulated_rel_l1_distance += tc.rescale_func(rel)
+                    if tc.accumulated_rel_l1_distance < tc.rel_l1_thresh:
+                        should_calc = False
+                    else:
+                        should_calc, tc.accumulated_rel_l1_distance = True, 0
+                tc.previous_modulated_input = e0_3
+                tc.cnt += 1
+                if tc.cnt == tc.num_steps:
+                    tc.reset()
+                tc.should_calc = should_calc
+            else:
+                should_calc = tc.should_calc
+            if not should_calc:                                                    # 1B.py:1049-1052
+                prev = tc.previous_residual_cond if cond_flag else tc.previous_residual_uncond
+                h = h + prev.to(h.device)
+            else:
+                ori = h.clone()
+                h = run_blocks(h)
+                res = h - ori
+                if tc.offload:
+                    res = res.cpu()
+                if cond_flag:
+                    tc.previous_residual_cond = res
+                else:
+                    tc.previous_residual_uncond = res
+        else:
+            h = run_blocks(h)
+
+        # head on the local tokens (1B.py:1154), then unpatchify; under SP gather the 64-wide head output instead of
+        # the hidden states (bit-identical to 1B.py:1150-1154, 24x less traffic)
+        em = ops.add_bcast(p["head_mod"], e_bf)                                     # [2, B, C]
+        rows_pb = h.shape[0] // B
+        xh = ops.layernorm(h, shift=em[0], scale=em[1], mod_bs=C, rows_per_batch=rows_pb)
+        u = ops.gemm(xh, self.head.head.weight, self.head.head.bias)
+        u = u.view(B, rows_pb, -1)
+        if P > 1:
+            from . import sequence_parallel as sp
+            u = sp.gather_tokens(self, u)
+        return ops.unpatchify(u, B, self.out_dim, F, H, W)
+
+    def _block(self, i, h, e, st):
+        """WanAttentionBlock.forward, 1B.py:650-695. h: [B*Ll, C] bf16 (Ll = local tokens), e: [B, 6C] bf16."""
+        blk, pb = self.blocks[i], self._prep["blocks"][i]
+        B, C, nh = st["B"], st["C"], st["nh"]
+        Ll = h.shape[0] // B
+        sa, ca = blk.self_attn, blk.cross_attn
+        ch = [e[:, k * C:(k + 1) * C] for k in range(6)]                           # views, batch stride 6C
+
+        # ---- self-attention (1B.py:383-413)
+        t1 = ops.layernorm(h, shift=ch[0], scale=ch[1], mod_bs=6 * C, rows_per_batch=Ll)
+        qkv = ops.gemm(t1, pb["w_qkv"], pb["b_qkv"])                               # [B*Ll, 3C]
+        if self.sp_world_size > 1:
+            from . import sequence_parallel as sp
+            a = sp.self_attention(self, qkv, sa, st)
+        else:
+            ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
+                              grid=st["grid"], rows_per_batch=Ll)
+            q4 = qkv.view(B, Ll, 3, nh, 128)
+            a = ops.flash_attn(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2])
+        ops.gemm(a.view(B * Ll, C), sa.o.weight, sa.o.bias, res=h, gate=ch[2], gate_ld=6 * C, rows_per_batch=Ll, out=h)
+
+        # ---- cross-attention: text + CLIP image + audio share q (1B.py:534-605)
+        xn = ops.layernorm(h, weight=blk.norm3.weight, bias=blk.norm3.bias)
+        q = ops.gemm(xn, ca.q.weight, ca.q.bias)
+        ops.rmsnorm_rope_(q, ca.norm_q.weight)
+        kv = ops.gemm(st["ctx_txt"], pb["w_kv"], pb["b_kv"])
+        ops.rmsnorm_rope_(kv[:, :C], ca.norm_k.weight)
+        kvi = ops.gemm(st["ctx_img"], pb["w_kv_img"], pb["b_kv_img"])
+        ops.rmsnorm_rope_(kvi[:, :C], ca.norm_k_img.weight)
+        vc = st["vc"]
+        kvv = ops.gemm(vc.view(-1, C), pb["w_kv_voc"], pb["b_kv_voc"])
+        q4 = q.view(B, Ll, nh, 128)
+        kv5 = kv.view(B, -1, 2, nh, 128)
+        kvi5 = kvi.view(B, -1, 2, nh, 128)
+        a = ops.flash_attn(q4, kv5[:, :, 0], kv5[:, :, 1])
+        ops.flash_attn(q4, kvi5[:, :, 0], kvi5[:, :, 1], out=a, accumulate=True)
+        if st["vc_grouped"]:
+            self._audio_attention(q, kvv, a, st, Ll)
+        else:
+            kvv5 = kvv.view(B, -1, 2, nh, 128)
+            ops.flash_attn(q4, kvv5[:, :, 0], kvv5[:, :, 1], out=a, accumulate=True)
+        ops.gemm(a.view(B * Ll, C), ca.o.weight, ca.o.bias, res=h, out=h)
+
+        # ---- FFN (1B.py:687-691)
+        t2 = ops.layernorm(h, shift=ch[3], scale=ch[4], mod_bs=6 * C, rows_per_batch=Ll)
+        hid = ops.gemm(t2, blk.ffn[0].weight, blk.ffn[0].bias, act=ops.ACT_GELU_TANH)
+        ops.gemm(hid, blk.ffn[2].weight, blk.ffn[2].bias, res=h, gate=ch[5], gate_ld=6 * C, rows_per_batch=Ll, out=h)
+        return h
+
+    def _audio_attention(self, q, kvv, a, st, Ll):
+        """Grouped audio cross-attention (1B.py:575-586): q.view(b*G, -1, n, d) pairs token group g with audio window g."""
+        B, C, nh, G = st["B"], st["C"], st["nh"], st["G"]
+        if self.sp_world_size > 1:
+            from . import sequence_parallel as sp
+            return sp.audio_attention(self, q, kvv, a, st, Ll)
+        if Ll % G != 0:
+            raise RuntimeError(f"shape '[{B * G}, -1, {nh}, 128]' is invalid for input of size {B * Ll * C}")
+        qg = q.view(B * G, Ll // G, nh, 128)
+        kg = kvv.view(B * G, -1, 2, nh, 128)
+        ops.flash_attn(qg, kg[:, :, 0], kg[:, :, 1], out=a.view(B * G, Ll // G, nh, 128), accumulate=True)
