@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — seconds per denoise step of the StableAvatar 1.3B audio-DiT at 480x832x81 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference algorithm (oracle port) on host cores
+
+A "step" is one denoise step of the pipeline loop body (wan/pipeline/wan_inference_long_pipeline.py:730-754): the DiT
+forward on the CFG batch of 3 (text/audio drop-outs), the 3-way CFG combine and the flow-matching Euler update.
+Prints ONE JSON line on rank 0. Weights are random-init of the named architecture and inputs synthetic (no network).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "s/denoise-step 1.3B @480x832x81f"
+UNIT = "s/step"
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(bf16=d["bf16_tflops_sustained"], bf16_burst=d["bf16_tflops"], hbm=d["hbm_gbs"], src="measured")
+    return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def workload(args):
+    F_lat, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
+    L = F_lat * (h // 2) * (w // 2)
+    return F_lat, h, w, L
+
+
+def step_flops(cfg, L, B=3, text=512, clip=257, G=21, A=15):
+    """SURVEY.md §8d algorithmic FLOPs of one denoise step (no padding, no recompute)."""
+    d, f, nl = cfg["dim"], cfg["ffn_dim"], cfg["num_layers"]
+    gemm = 2 * L * d * (6 * d + 2 * f) + 4 * d * d * (text + clip + G * A)
+    self_attn = 4 * L * L * d
+    cross = 4 * L * (text + clip + A) * d
+    adapter = 2 * (2 * 2 * L * d * d) + 2 * 4 * G * A * L // G * d
+    return B * nl * (gemm + self_attn + cross) + adapter, B * self_attn
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def cpu_block_sample(cfg, L, grid, threads=None):
+    """Time ONE WanAttentionBlock of the oracle (CPU restatement of 1B.py:650-695) at the full sequence length, B=1."""
+    from oracle import dit as O
+    from stableavatar_b200 import synth
+    if threads:
+        torch.set_num_threads(threads)
+    one = dict(cfg, num_layers=1)
+    shapes = {k: v for k, v in synth.dit_param_shapes(one).items() if k.startswith("blocks.0.")}
+    g = torch.Generator().manual_seed(0)
+    sd = {k: torch.randn(v, generator=g) * (0.02 if len(v) < 2 or k.endswith("bias") else v[-1] ** -0.5) for k, v in shapes.items()}
+    d = cfg["dim"]
+    x = torch.randn(1, L, d, generator=g)
+    e0 = torch.randn(1, 6, d, generator=g) * 0.1
+    ctx = torch.randn(1, 257 + 512, d, generator=g)
+    G = grid[0]
+    vc = torch.randn(1, G, 15, d, generator=g)
+    freqs = O.rope_freqs(d // cfg["num_heads"])
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.dit_block(sd, "blocks.0.", x, e0, [grid], freqs, ctx, vc, G, cfg["num_heads"])
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores. The Python reference cannot travel to the GPU box
+    (no /root/reference there), so this is the oracle port (oracle/dit.py, pinned to the real reference by
+    tests/golden). Each step = one block at full L, B=1, extrapolated x layers x CFG batch."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from stableavatar_b200 import synth
+    cfg = synth.DIT_1_3B
+    F_lat, h, w, L = workload(args)
+    cores = torch.get_num_threads()
+    steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    for _ in range(warm):
+        cpu_block_sample(cfg, L, (F_lat, h // 2, w // 2))
+    ts = [cpu_block_sample(cfg, L, (F_lat, h // 2, w // 2)) for _ in range(steps)]
+    per_block = sum(ts) / len(ts)
+    value = per_block * cfg["num_layers"] * 3
+    sample = (f"1 WanAttentionBlock (oracle port, fp32) at L={L}, B=1: {per_block:.2f} s measured; "
+              f"x{cfg['num_layers']} blocks x3 CFG samples extrapolated; {steps} timed / {warm} warm-up samples")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"1.3B audio-DiT denoise step, {args.height}x{args.width}x{args.frames}f, CFG batch 3, L={L}"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- B200 arm
+def build_model(cfg, device):
+    from stableavatar_b200.wan_transformer3d import WanTransformer3DFantasyModel
+    keys = ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim", "out_dim",
+            "num_heads", "num_layers")
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(device):
+            m = WanTransformer3DFantasyModel(**{k: cfg[k] for k in keys})
+    finally:
+        torch.set_default_dtype(old)
+    return m.init_random_(seed=0)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from stableavatar_b200 import _lib as L_, ops, synth
+    from stableavatar_b200.pipeline import WanI2VTalkingInferenceLongPipeline
+    from stableavatar_b200.scheduler import FlowMatchEulerDiscreteScheduler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = synth.DIT_1_3B
+    F_lat, h, w, L = workload(args)
+    model = build_model(cfg, dev)
+    if world > 1:
+        model.enable_multi_gpus_inference()
+    sched = FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=5.0)
+    sched.set_timesteps(50, device=dev)
+    pipe = WanI2VTalkingInferenceLongPipeline(transformer=model, scheduler=sched)
+
+    # synthetic conditioning of the pipeline's shapes, first in pinned host memory
+    inp = synth.dit_inputs(cfg, frames=args.frames, height=args.height, width=args.width, text_tokens=64)
+    bf = torch.bfloat16
+    host = dict(latents=inp["x"][:1].to(bf), y=inp["y"].to(bf), clip=inp["clip_fea"].to(bf), audio=inp["vocal_embeddings"].to(bf),
+                ctx=[c.to(bf) for c in inp["context"]])
+    host = {k: ([t.pin_memory() for t in v] if isinstance(v, list) else v.pin_memory()) for k, v in host.items()}
+    h2d_bytes = sum(t.numel() * 2 for t in (host["latents"], host["y"], host["clip"], host["audio"])) + \
+        sum(t.numel() * 2 for t in host["ctx"])
+    out_host = torch.empty_like(host["latents"]).pin_memory()
+
+    def to_dev():
+        return dict(latents=host["latents"].to(dev, non_blocking=True), y=host["y"].to(dev, non_blocking=True),
+                    clip=host["clip"].to(dev, non_blocking=True), audio=host["audio"].to(dev, non_blocking=True),
+                    ctx=[c.to(dev, non_blocking=True) for c in host["ctx"]])
+
+    def step(d, i):
+        t = sched._timesteps_host[i % 50]
+        return pipe.denoise_step(d["latents"], t, sched.dsigma_at(i % 50), d["ctx"], d["clip"], d["y"], d["audio"], seq_len=L,
+                                 clip_length=args.frames, text_guide_scale=3.0, audio_guide_scale=5.0, do_cfg=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    resident = to_dev()
+    for i in range(args.warmup):
+        step(resident, i)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ("value")
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ops.TIMING = {}
+    L_.launch_count = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(resident, i)
+    e1.record()
+    barrier()
+    launches = L_.launch_count
+    timing, ops.TIMING = ops.TIMING, None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    clocks = sampler.summary() if sampler else None
+
+    # ---- timed region 2: end to end through the pipeline API with host buffers ("e2e")
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        out_host.copy_(step(to_dev(), i), non_blocking=True)
+        torch.cuda.current_stream().synchronize()            # the caller reads the step's result on the host
+    e3.record()
+    barrier()
+    ms_e2e = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    s_per_step = ms.item() / 1e3 / args.steps
+    s_e2e = ms_e2e.item() / 1e3 / args.steps
+
+    if rank == 0:
+        peaks = load_peaks()
+        total_flops, attn_flops_per_launch = step_flops(cfg, L)
+        attn_ms = [a.elapsed_time(b) for a, b in timing.get("self_attn", [])]
+        attn_avg = sum(attn_ms) / max(1, len(attn_ms))
+        achieved = attn_flops_per_launch / world / (attn_avg * 1e-3) / 1e12 if attn_ms else None
+        shares = {k: sum(a.elapsed_time(b) for a, b in v) / (ms.item()) for k, v in timing.items()}
+        line = {
+            "metric": METRIC, "value": s_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"1.3B audio-DiT denoise step (30 blocks, CFG batch 3 + CFG/Euler), "
+                                   f"{args.height}x{args.width}x{args.frames}f, L={L}, text 512 + CLIP 257 + audio 21x15",
+                       "parallelism": f"sp{world}" if world > 1 else "single",
+                       "l2_policy": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
+                       "step_tflop": total_flops / 1e12,
+                       "step_tflops_achieved": total_flops / s_per_step / 1e12 / world,
+                       "bf16_peak_frac_step": total_flops / s_per_step / 1e12 / world / peaks["bf16"],
+                       "kernel_time_share": shares},
+            "roofline": {"kernel": "flash_attn_d128_kernel (self-attention)", "bound": "tensor", "achieved": achieved,
+                         "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"] if achieved else None,
+                         "traffic": None, "peak_source": f"{peaks['src']} sustained bf16 (MEASURED_PEAKS.json)",
+                         "launches_timed": len(attn_ms), "avg_launch_ms": attn_avg},
+            "e2e": {"value": s_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_host.numel() * 2},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = torch.get_num_threads()
+            per_block = cpu_block_sample(cfg, L, (F_lat, h // 2, w // 2))
+            line["cpu_baseline"] = {"value": per_block * cfg["num_layers"] * 3, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"1 WanAttentionBlock of the oracle port (fp32) at L={L}, B=1 measured "
+                                              f"{per_block:.2f} s; extrapolated x{cfg['num_layers']} blocks x3 CFG samples"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=81)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=832)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -109,7 +109,7 @@ int sa_layernorm_modulate(const sa_ln_args* args, sa_stream_t stream);
 
 /* ---- RMSNorm over the full channel dim (+ 3-D RoPE), in place on bf16 ------------------------------------------
  * x = bf16(bf16(x * rsqrt(mean(x^2) + eps)) * weight)          WanRMSNorm, 1B.py:326-342 (norm_q/norm_k/norm_k_img, vp1B norm_q/k)
- * then, if freqs != NULL, token t = row % rows_per_batch < F*H*W is rotated pairwise by freqs[pos][j] (cos, sin),
+ * then, if freqs != NULL, token t = tok_offset + row % rows_per_batch < F*H*W is rotated pairwise by freqs[pos][j] (cos, sin),
  * pos = frame / row / column index for j < 22 / < 43 / < 64       rope_apply, 1B.py:296-323; table 1B.py:855-862
  * Up to two segments (q and k of a fused QKV GEMM output) share the launch: x/weight and x2/weight2 (x2 may be NULL).
  * freqs: float [1024][64][2]. C % 8 == 0 (C % 128 == 0 with RoPE), ld % 8 == 0.
@@ -122,6 +122,7 @@ typedef struct {
   const void* freqs;
   int64_t ld;
   int32_t rows, C, rows_per_batch, F, H, W;
+  int32_t tok_offset; /* global index of this shard's first token (sequence parallelism), else 0 */
   float eps;
 } sa_rms_args;
 int sa_rmsnorm_rope(const sa_rms_args* args, sa_stream_t stream);

@@ -60,7 +60,12 @@ def lib() -> C.CDLL:
     return _lib
 
 
+launch_count = 0  # kernels of this library launched through the wrappers (bench.py reports it as gpu_launches)
+
+
 def check(rc: int, what: str) -> None:
+    global launch_count
+    launch_count += 1
     if rc != 0:
         raise RuntimeError(f"{what} failed (code {rc}): {lib().sa_last_error().decode()}")
 

@@ -2,10 +2,13 @@
 //
 //   out[M,N] = epilogue(A[M,K] . W[N,K]^T)          (both operands K-major == nn.Linear layout)
 //
-// One CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM owner), warps 2-5 = epilogue.
-// Tile 128 x 256 x 64, 4 smem stages (48 KB each, SWIZZLE_128B), fp32 accumulators double-buffered in TMEM
-// (2 x 256 columns) so tile i's epilogue overlaps tile i+1's MMAs. M/N/K tails are handled by TMA zero-fill on
-// the load side and by masking on the store side.
+// One CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM owner), warps 2-9 = epilogue
+// (two warps per TMEM lane quarter, each owning half of the tile's columns). Tile 128 x 256 x 64, 4 smem stages (48 KB
+// each, SWIZZLE_128B), fp32 accumulators double-buffered in TMEM (2 x 256 columns) so tile i's epilogue overlaps tile
+// i+1's MMAs. The epilogue is specialised at compile time on (activation, residual mode): bf16 results are staged in
+// shared memory in the 128-byte swizzle pattern and written with TMA stores (coalesced, M/N tails clipped by the
+// hardware); a generic run-time-switched epilogue with direct stores covers fp32 outputs and odd shapes.
+// M/N/K tails on the load side are TMA zero-fill.
 //
 // Replaces the nn.Linear calls of the reference (see include/stableavatar_b200.h for the file:line list).
 #include <stdio.h>
@@ -22,9 +25,11 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_BYTES = BN * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = (2 + EPI_WARPS) * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int PANEL_BYTES = 32 * 128;  // one epilogue warp's staging panel: 32 rows x 64 bf16 columns, SWIZZLE_128B
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * PANEL_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 
 struct Params {
   void* out;
@@ -54,6 +59,16 @@ __device__ __forceinline__ void load8(const void* base, int dtype, long long idx
     v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
 }
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
 __device__ __forceinline__ float load1(const void* base, int dtype, long long idx) {
   return dtype == SA_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx])
                           : reinterpret_cast<const float*>(base)[idx];
@@ -77,24 +92,44 @@ __device__ __forceinline__ void store1(void* base, int dtype, long long idx, flo
   else reinterpret_cast<float*>(base)[idx] = v;
 }
 
-__device__ __forceinline__ float apply_act(float y, int act) {
-  if (act == 1) {  // GELU(tanh): 0.5 y (1 + tanh(sqrt(2/pi) (y + 0.044715 y^3)))
-    float u = 0.7978845608028654f * (y + 0.044715f * y * y * y);
-    return 0.5f * y * (1.0f + tanh_approx(u));
-  } else if (act == 2) {  // SiLU
-    return y / (1.0f + __expf(-y));
-  } else if (act == 3) {  // GELU(erf)
+template <int ACT>
+__device__ __forceinline__ float act_fn(float y) {
+  if constexpr (ACT == 1) {  // GELU(tanh): 0.5 y (1 + tanh(sqrt(2/pi) (y + 0.044715 y^3)))
+    const float u = y * fmaf(0.7978845608028654f * 0.044715f, y * y, 0.7978845608028654f);
+    const float hy = 0.5f * y;
+    return fmaf(hy, tanh_approx(u), hy);
+  } else if constexpr (ACT == 2) {  // SiLU
+    return __fdividef(y, 1.0f + __expf(-y));
+  } else if constexpr (ACT == 3) {  // GELU(erf)
     return 0.5f * y * (1.0f + erff(y * 0.7071067811865476f));
+  } else {
+    return y;
   }
-  return y;
+}
+__device__ __forceinline__ float act_rt(float y, int act) {
+  return act == 1 ? act_fn<1>(y) : (act == 2 ? act_fn<2>(y) : (act == 3 ? act_fn<3>(y) : y));
 }
 
+// TMA store of one staged panel (global <- shared), bulk-group completion.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// FAST: bf16 output through swizzled smem staging + TMA store, bf16 bias/res, bf16 rounding of the Linear output
+// (autocast), ACT / RES fixed at compile time. !FAST: everything decided at run time, direct global stores.
+template <bool FAST, int ACT, int RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const Params p) {
+                 const __grid_constant__ CUtensorMap tmap_c, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* stage_out = smem + STAGES * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_out + EPI_WARPS * PANEL_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;  // accumulator stage ready for the epilogue
   uint64_t* tempty = tfull + 2;      // accumulator stage drained by the epilogue
@@ -108,6 +143,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (FAST) tma_prefetch_desc(&tmap_c);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -117,7 +153,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull[s], 1);
-        mbar_init(&tempty[s], 4);
+        mbar_init(&tempty[s], EPI_WARPS);
       }
       fence_barrier_init();
     }
@@ -177,8 +213,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5, TMEM lane quarter = warp % 4)
-    const int q = warp & 3;
+    // ------------------------------------------------------------ epilogue: warps 2..9
+    const int ew = warp - 2;
+    const int q = warp & 3;        // TMEM lane quarter this warp may read
+    const int half = ew >> 2;      // which 128 of the tile's 256 columns
+    uint8_t* panel = stage_out + ew * PANEL_BYTES;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int m0 = (tile / p.tiles_n) * BM;
@@ -188,72 +227,96 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const long long gate_row = (p.res_mode == 2 && row_ok) ? (long long)(row / p.rows_per_batch) * p.gate_ld : 0;
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * 128;
+
+      if constexpr (FAST) {
+        const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(p.bias);
+        const __nv_bfloat16* res_row =
+            RES ? reinterpret_cast<const __nv_bfloat16*>(p.res) + (long long)(row_ok ? row : 0) * p.ldr : nullptr;
+        const __nv_bfloat16* gate_row =
+            RES == 2 ? reinterpret_cast<const __nv_bfloat16*>(p.gate) + (long long)((row_ok ? row : 0) / p.rows_per_batch) * p.gate_ld
+                     : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int nc = n0 + c * 32;
-        if (nc >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_x32(tmem_base + (uint32_t(q * 32) << 16) + as * BN + c * 32, r);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        if (nc + 32 <= p.N) {
+        for (int pn = 0; pn < 2; ++pn) {  // two 64-column panels
+          const int nc = n0 + half * 128 + pn * 64;
+          if (nc >= p.N) break;  // warp-uniform
+          uint32_t r0[32], r1[32];
+          tmem_ld_x32(t_row + pn * 64, r0);
+          tmem_ld_x32(t_row + pn * 64 + 32, r1);
+          tmem_ld_wait();
+          if (lane == 0) bulk_wait_read0();  // previous TMA store has finished reading this warp's panel
+          __syncwarp();
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            const int n = nc + j8 * 8;
+          for (int c8 = 0; c8 < 8; ++c8) {  // 8 chunks of 8 columns = 16 bytes of bf16 each
+            const int n = nc + c8 * 8;
             float y[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(r[j8 * 8 + i]);
-            if (p.bias) {
+            for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(c8 < 4 ? r0[c8 * 8 + i] : r1[(c8 - 4) * 8 + i]);
+            const bool col_ok = n < p.N;  // N % 8 == 0 on this path
+            if (bias != nullptr && col_ok) {
               float b[8];
-              load8(p.bias, p.bias_dtype, n, b);
+              load8_bf16(bias + n, b);
 #pragma unroll
               for (int i = 0; i < 8; ++i) y[i] += b[i];
             }
-            if (p.round_y) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) y[i] = bf16_round(y[i]);
+            for (int i = 0; i < 8; ++i) y[i] = bf16_round(y[i]);
+            if constexpr (ACT != 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = act_fn<ACT>(y[i]);
             }
-            if (p.act) {
+            if constexpr (RES != 0) {
+              if (row_ok && col_ok) {
+                float rs[8];
+                load8_bf16(res_row + n, rs);
+                if constexpr (RES == 2) {
+                  float g[8];
+                  load8_bf16(gate_row + n, g);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                y[i] = apply_act(y[i], p.act);
-                if (p.round_y) y[i] = bf16_round(y[i]);
-              }
-            }
-            if (p.res_mode) {
-              float rs[8];
-              load8(p.res, p.res_dtype, (long long)row * p.ldr + n, rs);
-              if (p.res_mode == 2) {
-                float g[8];
-                load8(p.gate, SA_BF16, gate_row + n, g);
+                  for (int i = 0; i < 8; ++i) y[i] = rs[i] + bf16_round(bf16_round(y[i]) * g[i]);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float t = y[i] * g[i];
-                  if (p.round_y) t = bf16_round(t);
-                  y[i] = rs[i] + t;
+                  for (int i = 0; i < 8; ++i) y[i] = rs[i] + bf16_round(y[i]);
                 }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = rs[i] + y[i];
               }
             }
-            store8(p.out, p.out_dtype, (long long)row * p.ldc + n, y);
+            uint4 u;
+            u.x = pack_bf16x2(y[0], y[1]);
+            u.y = pack_bf16x2(y[2], y[3]);
+            u.z = pack_bf16x2(y[4], y[5]);
+            u.w = pack_bf16x2(y[6], y[7]);
+            *reinterpret_cast<uint4*>(panel + lane * 128 + ((c8 ^ (lane & 7)) << 4)) = u;
           }
-        } else {
-#pragma unroll
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_c, panel, nc, m0 + q * 32);
+            bulk_commit();
+          }
+        }
+      } else {
+        const long long gate_row = (p.res_mode == 2 && row_ok) ? (long long)(row / p.rows_per_batch) * p.gate_ld : 0;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int nc = n0 + half * 128 + c * 32;
+          if (nc >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+#pragma unroll 1
           for (int j = 0; j < 32; ++j) {
             const int n = nc + j;
-            if (n >= p.N) continue;
+            if (n >= p.N) break;
             float y = __uint_as_float(r[j]);
             if (p.bias) y += load1(p.bias, p.bias_dtype, n);
             if (p.round_y) y = bf16_round(y);
             if (p.act) {
-              y = apply_act(y, p.act);
+              y = act_rt(y, p.act);
               if (p.round_y) y = bf16_round(y);
             }
             if (p.res_mode) {
-              float rs = load1(p.res, p.res_dtype, (long long)row * p.ldr + n);
+              const float rs = load1(p.res, p.res_dtype, (long long)row * p.ldr + n);
               if (p.res_mode == 2) {
                 float t = y * load1(p.gate, SA_BF16, gate_row + n);
                 if (p.round_y) t = bf16_round(t);
@@ -270,6 +333,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
     }
+    if (FAST && lane == 0) bulk_wait0();  // all of this warp's TMA stores have landed before the CTA retires
   }
 
   tc_fence_before();
@@ -278,6 +342,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+template <bool FAST, int ACT, int RES>
+static int launch(const CUtensorMap& tma, const CUtensorMap& tmb, const CUtensorMap& tmc, const Params& p, int grid,
+                  cudaStream_t stream) {
+  static bool attr_set = false;
+  auto* kern = gemm_bf16_kernel<FAST, ACT, RES>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_bf16_kernel)");
+    attr_set = true;
+  }
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tma, tmb, tmc, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "gemm_bf16_kernel launch");
+  return SA_OK;
 }
 
 }  // namespace gemm
@@ -294,12 +374,6 @@ extern "C" int sa_gemm_bf16(const sa_gemm_args* a, sa_stream_t stream_) {
               (long long)a->lda, (long long)a->ldw);
     return SA_ERR_BAD_ARG;
   }
-  if (a->N % 8 == 0) {
-    if (a->ldc % 8 || (a->res_mode && a->ldr % 8) || (a->res_mode == 2 && a->gate_ld % 8)) {
-      set_error("sa_gemm_bf16: ldc/ldr/gate_ld must be multiples of 8");
-      return SA_ERR_BAD_ARG;
-    }
-  }
   if (a->res_mode && !a->res) { set_error("sa_gemm_bf16: res_mode set but res is null"); return SA_ERR_BAD_ARG; }
   if (a->res_mode == 2 && (!a->gate || a->rows_per_batch <= 0)) {
     set_error("sa_gemm_bf16: gated residual needs gate and rows_per_batch > 0");
@@ -310,7 +384,7 @@ extern "C" int sa_gemm_bf16(const sa_gemm_args* a, sa_stream_t stream_) {
     return SA_ERR_BAD_ARG;
   }
 
-  CUtensorMap tma, tmb;
+  CUtensorMap tma, tmb, tmc;
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
     uint64_t strides[1] = {(uint64_t)a->lda * 2};
@@ -325,6 +399,27 @@ extern "C" int sa_gemm_bf16(const sa_gemm_args* a, sa_stream_t stream_) {
     int rc = make_tmap_bf16(&tmb, a->w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  // Fast path: bf16 everywhere, autocast rounding, 16-byte aligned rows.
+  const bool fast = a->out_dtype == SA_BF16 && a->round_y && a->N % 8 == 0 && a->ldc % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (!a->bias || a->bias_dtype == SA_BF16) &&
+                    (!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) &&
+                    (a->res_mode == 0 || (a->res_dtype == SA_BF16 && a->ldr % 8 == 0 &&
+                                          (reinterpret_cast<uintptr_t>(a->res) & 15) == 0)) &&
+                    (a->res_mode != 2 || (a->gate_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->gate) & 15) == 0)) &&
+                    (a->act == 0 || a->act == 1 || (a->act == 3 && a->res_mode == 0));
+  if (fast) {
+    uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
+    uint64_t strides[1] = {(uint64_t)a->ldc * 2};
+    uint32_t box[2] = {64, 32};
+    int rc = make_tmap_bf16(&tmc, a->out, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else {
+    tmc = tma;
+    if (a->N % 8 == 0 && (a->ldc % 4 || (a->res_mode && a->ldr % 4))) {
+      set_error("sa_gemm_bf16: ldc/ldr must be multiples of 4");
+      return SA_ERR_BAD_ARG;
+    }
+  }
   Params p;
   p.out = a->out; p.bias = a->bias; p.res = a->res; p.gate = a->gate;
   p.ldc = a->ldc; p.ldr = a->ldr; p.gate_ld = a->gate_ld;
@@ -334,17 +429,17 @@ extern "C" int sa_gemm_bf16(const sa_gemm_args* a, sa_stream_t stream_) {
   p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : a->M;
   p.tiles_m = (a->M + BM - 1) / BM;
   p.tiles_n = (a->N + BN - 1) / BN;
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_bf16_kernel)");
-    attr_set = true;
-  }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tma, tmb, p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "gemm_bf16_kernel launch");
-  return SA_OK;
+
+  if (!fast) return launch<false, 0, 0>(tma, tmb, tmc, p, grid, stream);
+  if (a->act == 3) return launch<true, 3, 0>(tma, tmb, tmc, p, grid, stream);
+  if (a->act == 1) {
+    if (a->res_mode == 0) return launch<true, 1, 0>(tma, tmb, tmc, p, grid, stream);
+    if (a->res_mode == 1) return launch<true, 1, 1>(tma, tmb, tmc, p, grid, stream);
+    return launch<true, 1, 2>(tma, tmb, tmc, p, grid, stream);
+  }
+  if (a->res_mode == 0) return launch<true, 0, 0>(tma, tmb, tmc, p, grid, stream);
+  if (a->res_mode == 1) return launch<true, 0, 1>(tma, tmb, tmc, p, grid, stream);
+  return launch<true, 0, 2>(tma, tmb, tmc, p, grid, stream);
 }

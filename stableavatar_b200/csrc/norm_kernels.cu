@@ -150,7 +150,7 @@ struct RmsParams {
   const __nv_bfloat16* weight[2];
   const float2* freqs;  // [1024][64] (cos, sin), NULL = no rotation
   long long ld;
-  int rows, C, rows_per_batch, F, H, W;
+  int rows, C, rows_per_batch, F, H, W, tok_offset;
   float eps;
 };
 
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) rmsnorm_rope_kernel(cons
     }
   }
   const float rinv = rsqrtf(warp_sum(ss) / p.C + p.eps);
-  const int tok = row % p.rows_per_batch;
+  const int tok = row % p.rows_per_batch + p.tok_offset;
   const bool rotate = p.freqs != nullptr && tok < p.F * p.H * p.W;
   const int pf = tok / (p.H * p.W), ph = (tok / p.W) % p.H, pw = tok % p.W;
 #pragma unroll
@@ -278,7 +278,7 @@ extern "C" int sa_rmsnorm_rope(const sa_rms_args* a, sa_stream_t stream_) {
   p.freqs = reinterpret_cast<const float2*>(a->freqs);
   p.ld = a->ld; p.rows = a->rows; p.C = a->C;
   p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : a->rows;
-  p.F = a->F; p.H = a->H; p.W = a->W; p.eps = a->eps;
+  p.F = a->F; p.H = a->H; p.W = a->W; p.tok_offset = a->tok_offset; p.eps = a->eps;
   dim3 grid((a->rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, a->x2 ? 2 : 1);
   const int nch = (a->C / 8 + 31) / 32;
   if (nch <= 2) rmsnorm_rope_kernel<2><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);

@@ -11,6 +11,27 @@ from . import _lib as L
 from ._lib import ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_SILU  # noqa: F401
 
 
+TIMING = None  # set to {} to collect (start, end) CUDA-event pairs per tag on the launching stream (bench.py)
+
+
+class timed:
+    """with ops.timed("self_attn"): ... — brackets the enclosed launches with CUDA events when ops.TIMING is a dict."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if TIMING is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            TIMING.setdefault(self.tag, []).append((self.e0, e1))
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -107,10 +128,12 @@ def layernorm(x, *, weight=None, bias=None, shift=None, scale=None, gate=None, r
 class RmsArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("weight", C.c_void_p), ("x2", C.c_void_p), ("weight2", C.c_void_p),
                 ("freqs", C.c_void_p), ("ld", C.c_int64), ("rows", C.c_int32), ("C", C.c_int32),
-                ("rows_per_batch", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("eps", C.c_float)]
+                ("rows_per_batch", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("tok_offset", C.c_int32),
+                ("eps", C.c_float)]
 
 
-def rmsnorm_rope_(x, weight, x2=None, weight2=None, freqs=None, grid=(1, 1, 1), rows_per_batch=0, eps=1e-6):
+def rmsnorm_rope_(x, weight, x2=None, weight2=None, freqs=None, grid=(1, 1, 1), rows_per_batch=0, eps=1e-6,
+                  tok_offset=0):
     """In-place RMSNorm (+RoPE) on one or two bf16 row views sharing a row stride — sa_rmsnorm_rope."""
     _need_cuda(x)
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
@@ -120,7 +143,7 @@ def rmsnorm_rope_(x, weight, x2=None, weight2=None, freqs=None, grid=(1, 1, 1), 
         assert freqs.dtype == torch.float32 and freqs.shape == (1024, 64, 2) and freqs.is_contiguous()
     a = RmsArgs(x=x.data_ptr(), weight=weight.data_ptr(), x2=L.ptr(x2), weight2=L.ptr(weight2), freqs=L.ptr(freqs),
                 ld=x.stride(0), rows=x.shape[0], C=x.shape[1], rows_per_batch=rows_per_batch, F=grid[0], H=grid[1],
-                W=grid[2], eps=eps)
+                W=grid[2], tok_offset=tok_offset, eps=eps)
     L.check(L.lib().sa_rmsnorm_rope(C.byref(a), L.stream_ptr()), "sa_rmsnorm_rope")
     return x
 

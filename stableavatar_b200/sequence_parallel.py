@@ -1,0 +1,139 @@
+"""Sequence parallelism for the DiT over one NVSwitch domain: one process per GPU, tokens sharded contiguously along L.
+
+Replaces the reference's xfuser path (wan/dist/wan_xfuser.py:72-114 `usp_attn_forward`, `enable_multi_gpus_inference`
+wan_fantasy_transformer3d_1B.py:918-923, token chunking :1018-1019, final gather :1150-1151). Everything except
+self-attention is token-local; self-attention exchanges heads for sequence with an all-to-all (Ulysses):
+
+  P | num_heads  : pure Ulysses — rank r attends all tokens for heads [r*hp, (r+1)*hp).
+  otherwise      : hg = gcd(num_heads, P) head groups x qs = P/hg query splits (12 heads on 8 GPUs -> 4 x 2): rank
+                   (g, s) receives K, V of head group g from every rank but Q only from ranks r' with r' % qs == s, so
+                   FLOPs stay balanced and no softmax merge (ring / LSE) is needed.
+
+Semantics are those of the SINGLE-GPU reference (SURVEY.md fact #9-iii): RoPE positions and audio-window groups are
+computed from the global token index, unlike the reference's SP path which pairs local token groups with the wrong audio
+windows. L must be a multiple of P (the model rounds seq_len up, 1B.py:980-981).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def plan(num_heads: int, world: int, rank: int) -> SimpleNamespace:
+    hg = math.gcd(num_heads, world)
+    qs = world // hg
+    return SimpleNamespace(world=world, rank=rank, hg=hg, qs=qs, hp=num_heads // hg, g=rank // qs, s=rank % qs,
+                           q_sources=[r for r in range(world) if r % qs == rank % qs])
+
+
+def all_to_all(outputs, inputs, group=None):
+    """List all-to-all (ragged allowed). NCCL: one grouped collective over NVLink. gloo (CPU tests): isend/irecv."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(outputs, inputs, group=group)
+        return
+    rank = dist.get_rank(group)
+    outputs[rank].copy_(inputs[rank])
+    reqs = []
+    for r in range(dist.get_world_size(group)):
+        if r == rank:
+            continue
+        peer = dist.get_global_rank(group, r) if group is not None else r
+        if inputs[r].numel():
+            reqs.append(dist.isend(inputs[r].contiguous(), peer, group=group))
+        if outputs[r].numel():
+            reqs.append(dist.irecv(outputs[r], peer, group=group))
+    for q in reqs:
+        q.wait()
+
+
+def exchange_qkv(pl, q, k, v, group=None):
+    """q, k, v: local [B, Ll, nh, d] views. Returns (Q [Lq, B, hp, d], KV [L, B, 2, hp, d]) for this rank's head group:
+    all tokens for K/V, the tokens of `pl.q_sources` (in rank order) for Q. Token-major so that the token stride is
+    uniform for the attention kernel's TMA descriptors."""
+    B, Ll, nh, d = q.shape
+    P, hp = pl.world, pl.hp
+    send, recv = [], []
+    for dst in range(P):
+        g, s = dst // pl.qs, dst % pl.qs
+        hs = slice(g * hp, (g + 1) * hp)
+        kv = torch.stack([k[:, :, hs], v[:, :, hs]], dim=2).permute(1, 0, 2, 3, 4)          # [Ll, B, 2, hp, d]
+        parts = [kv.reshape(-1)]
+        if pl.rank % pl.qs == s:
+            parts.append(q[:, :, hs].permute(1, 0, 2, 3).reshape(-1))
+        send.append(torch.cat(parts))
+    n_kv, n_q = Ll * B * 2 * hp * d, Ll * B * hp * d
+    for src in range(P):
+        recv.append(torch.empty(n_kv + (n_q if src in pl.q_sources else 0), device=q.device, dtype=q.dtype))
+    all_to_all(recv, send, group)
+    KV = torch.stack([r[:n_kv].view(Ll, B, 2, hp, d) for r in recv]).view(P * Ll, B, 2, hp, d)
+    Q = torch.stack([recv[src][n_kv:].view(Ll, B, hp, d) for src in pl.q_sources]).view(len(pl.q_sources) * Ll, B, hp, d)
+    return Q, KV
+
+
+def exchange_out(pl, O, B, Ll, nh, d, group=None):
+    """O: [Lq, B, hp, d] attention output of this rank (its head group, the tokens of pl.q_sources). Returns the local
+    [B, Ll, nh, d] with every head group filled in by its owner."""
+    P, hp = pl.world, pl.hp
+    n = Ll * B * hp * d
+    Os = O.view(len(pl.q_sources), Ll, B, hp, d)
+    send = [Os[pl.q_sources.index(dst)].reshape(-1) if dst in pl.q_sources else O.new_empty(0) for dst in range(P)]
+    recv = [O.new_empty(n if src % pl.qs == pl.rank % pl.qs else 0) for src in range(P)]
+    all_to_all(recv, send, group)
+    out = O.new_empty(B, Ll, nh, d)
+    for src in range(P):
+        if recv[src].numel():
+            g = src // pl.qs
+            out[:, :, g * hp:(g + 1) * hp] = recv[src].view(Ll, B, hp, d).permute(1, 0, 2, 3)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- model hooks
+def shard_tokens(model, h, st):
+    """1B.py:1018-1019: keep this rank's contiguous chunk of the (padded) token sequence."""
+    B, L, C = st["B"], st["L"], st["C"]
+    P, r = model.sp_world_size, model.sp_world_rank
+    Ll = L // P
+    st = dict(st, Ll=Ll, tok0=r * Ll)
+    return h.view(B, L, C)[:, r * Ll:(r + 1) * Ll].reshape(B * Ll, C).contiguous(), st
+
+
+def self_attention(model, qkv, sa, st):
+    """xf.py:72-114 with global RoPE positions: RMSNorm+RoPE on the local shard, all-to-all, attention over the full
+    sequence for this rank's heads, all-to-all back. Returns [B, Ll, nh, 128]."""
+    B, C, nh, Ll = st["B"], st["C"], st["nh"], st["Ll"]
+    pl = model._sp
+    ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
+                      grid=st["grid"], rows_per_batch=Ll, tok_offset=st["tok0"])
+    q5 = qkv.view(B, Ll, 3, nh, 128)
+    Q, KV = exchange_qkv(pl, q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], model.sp_group)
+    with ops.timed("self_attn"):
+        O = ops.flash_attn(Q.transpose(0, 1), KV[:, :, 0].transpose(0, 1), KV[:, :, 1].transpose(0, 1),
+                           out=torch.empty_like(Q).transpose(0, 1))
+    return exchange_out(pl, O.transpose(0, 1), B, Ll, nh, 128, model.sp_group)
+
+
+def audio_attention(model, q, kvv, a, st, Ll):
+    """Grouped audio cross-attention on a token shard: global token t belongs to audio window t // (L/G) (the
+    single-GPU view(b*G, ...) of 1B.py:575-586); a shard straddles a few windows, one launch per window."""
+    B, C, nh, G, L, tok0 = st["B"], st["C"], st["nh"], st["G"], st["L"], st["tok0"]
+    if L % G != 0:
+        raise RuntimeError(f"shape '[{B * G}, -1, {nh}, 128]' is invalid for input of size {B * L * C}")
+    gs = L // G
+    q4, a4 = q.view(B, Ll, nh, 128), a.view(B, Ll, nh, 128)
+    kg = kvv.view(B, G, -1, 2, nh, 128)
+    for g in range(tok0 // gs, (tok0 + Ll - 1) // gs + 1):
+        lo, hi = max(g * gs, tok0) - tok0, min((g + 1) * gs, tok0 + Ll) - tok0
+        ops.flash_attn(q4[:, lo:hi], kg[:, g, :, 0], kg[:, g, :, 1], out=a4[:, lo:hi], accumulate=True)
+
+
+def gather_tokens(model, u):
+    """Gather the 64-wide head output of every shard (instead of the 1536-wide hidden states, 1B.py:1150-1154)."""
+    P = model.sp_world_size
+    parts = [torch.empty_like(u) for _ in range(P)]
+    dist.all_gather(parts, u.contiguous(), group=model.sp_group)
+    return torch.cat(parts, dim=1)

@@ -40,7 +40,7 @@ def fill_state_dict(shapes: dict, seed: int = 0) -> dict:
             sd[name] = det_normal(name, shape, std=shape[-1] ** -0.5, seed=seed)
         elif name.endswith(".bias"):
             sd[name] = det_normal(name, shape, std=0.02, seed=seed)
-        elif len(shape) == 1:
+        elif len(shape) == 1 or name.endswith(".gamma"):
             sd[name] = det_normal(name, shape, std=0.1, mean=1.0, seed=seed)
         else:
             fan_in = int(np.prod(shape[1:]))
@@ -138,3 +138,70 @@ def dit_inputs(cfg: dict, frames: int, height: int, width: int, batch: int = 3, 
                 t=torch.full((batch,), t_value), context=context,
                 clip_fea=det_normal("clip_fea", (1, 257, 1280), seed=seed).expand(batch, -1, -1).contiguous(),
                 vocal_embeddings=vocal, seq_len=F_lat * (h // 2) * (w // 2), video_sample_n_frames=frames)
+
+
+# ---------------------------------------------------------------------------------------------- Wan VAE (decode side)
+def vae_decoder_layout(dim=96, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_upsample=(True, True, False)):
+    """Module list of Decoder3d.upsamples (wan/models/wan_vae.py:391-418): ('res', cin, cout) / ('up3d'|'up2d', c)."""
+    dims = [dim * u for u in [dim_mult[-1]] + list(dim_mult[::-1])]
+    mods = []
+    for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+        if i in (1, 2, 3):
+            cin = cin // 2
+        for _ in range(num_res_blocks + 1):
+            mods.append(("res", cin, cout))
+            cin = cout
+        if i != len(dim_mult) - 1:
+            mods.append(("up3d" if temperal_upsample[i] else "up2d", cout))
+    return dims, mods
+
+
+def vae_decoder_param_shapes(dim=96, z_dim=16, dim_mult=(1, 2, 4, 4)):
+    """Names/shapes of the decode-side parameters of AutoencoderKLWan (wan/models/wan_vae.py:372-424, 516-518), checked
+    against the real module by tools/gen_golden.py."""
+    dims, mods = vae_decoder_layout(dim, dim_mult)
+    s = {"model.conv2.weight": (z_dim, z_dim, 1, 1, 1), "model.conv2.bias": (z_dim,)}
+    p = "model.decoder."
+    s[p + "conv1.weight"] = (dims[0], z_dim, 3, 3, 3)
+    s[p + "conv1.bias"] = (dims[0],)
+
+    def res(pre, cin, cout):
+        s[pre + "residual.0.gamma"] = (cin, 1, 1, 1)
+        s[pre + "residual.2.weight"] = (cout, cin, 3, 3, 3)
+        s[pre + "residual.2.bias"] = (cout,)
+        s[pre + "residual.3.gamma"] = (cout, 1, 1, 1)
+        s[pre + "residual.6.weight"] = (cout, cout, 3, 3, 3)
+        s[pre + "residual.6.bias"] = (cout,)
+        if cin != cout:
+            s[pre + "shortcut.weight"] = (cout, cin, 1, 1, 1)
+            s[pre + "shortcut.bias"] = (cout,)
+
+    res(p + "middle.0.", dims[0], dims[0])
+    s[p + "middle.1.norm.gamma"] = (dims[0], 1, 1)
+    s[p + "middle.1.to_qkv.weight"] = (3 * dims[0], dims[0], 1, 1)
+    s[p + "middle.1.to_qkv.bias"] = (3 * dims[0],)
+    s[p + "middle.1.proj.weight"] = (dims[0], dims[0], 1, 1)
+    s[p + "middle.1.proj.bias"] = (dims[0],)
+    res(p + "middle.2.", dims[0], dims[0])
+    c_last = dims[0]
+    for i, m in enumerate(mods):
+        q = f"{p}upsamples.{i}."
+        if m[0] == "res":
+            res(q, m[1], m[2])
+            c_last = m[2]
+        else:
+            c = m[1]
+            s[q + "resample.1.weight"] = (c // 2, c, 3, 3)
+            s[q + "resample.1.bias"] = (c // 2,)
+            if m[0] == "up3d":
+                s[q + "time_conv.weight"] = (2 * c, c, 3, 1, 1)
+                s[q + "time_conv.bias"] = (2 * c,)
+            c_last = c // 2
+    s[p + "head.0.gamma"] = (c_last, 1, 1, 1)
+    s[p + "head.2.weight"] = (3, c_last, 3, 3, 3)
+    s[p + "head.2.bias"] = (3,)
+    return s
+
+
+def vae_state_dict(seed: int = 0, **kw) -> dict:
+    return fill_state_dict(vae_decoder_param_shapes(**kw), seed)

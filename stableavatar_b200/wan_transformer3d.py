@@ -193,6 +193,27 @@ class WanTransformer3DFantasyModel(nn.Module):
         self.vocal_projector._prep = None
         return super()._apply(fn, *a, **k)
 
+    @torch.no_grad()
+    def init_random_(self, seed=0):
+        """Synthetic weights drawn on the parameters' own device (bench.py: no checkpoints exist offline): matrices
+        ~ N(0, 1/fan_in), biases ~ N(0, 0.02^2), norm scales ~ N(1, 0.1^2) — the distribution of synth.fill_state_dict,
+        including non-zero k_vocal / v_vocal so the audio cross-attention does real work."""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        for name, prm in self.named_parameters():
+            r = torch.randn(prm.shape, generator=g, device=prm.device, dtype=torch.float32)
+            if name.endswith("modulation"):
+                r *= prm.shape[-1] ** -0.5
+            elif name.endswith(".bias"):
+                r *= 0.02
+            elif prm.dim() == 1:
+                r = 1.0 + 0.1 * r
+            else:
+                r *= float(np.prod(prm.shape[1:])) ** -0.5
+            prm.copy_(r)
+        self._prep = None
+        self.vocal_projector._prep = None
+        return self
+
     # ------------------------------------------------------------------ one-time operand preparation
     def _prepare(self):
         if self._prep is not None:
@@ -369,7 +390,8 @@ class WanTransformer3DFantasyModel(nn.Module):
 
         # ---- self-attention (1B.py:383-413)
         t1 = ops.layernorm(h, shift=ch[0], scale=ch[1], mod_bs=6 * C, rows_per_batch=Ll)
-        qkv = ops.gemm(t1, pb["w_qkv"], pb["b_qkv"])                               # [B*Ll, 3C]
+        with ops.timed("qkv_gemm"):
+            qkv = ops.gemm(t1, pb["w_qkv"], pb["b_qkv"])                           # [B*Ll, 3C]
         if self.sp_world_size > 1:
             from . import sequence_parallel as sp
             a = sp.self_attention(self, qkv, sa, st)
@@ -377,7 +399,8 @@ class WanTransformer3DFantasyModel(nn.Module):
             ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
                               grid=st["grid"], rows_per_batch=Ll)
             q4 = qkv.view(B, Ll, 3, nh, 128)
-            a = ops.flash_attn(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2])
+            with ops.timed("self_attn"):
+                a = ops.flash_attn(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2])
         ops.gemm(a.view(B * Ll, C), sa.o.weight, sa.o.bias, res=h, gate=ch[2], gate_ld=6 * C, rows_per_batch=Ll, out=h)
 
         # ---- cross-attention: text + CLIP image + audio share q (1B.py:534-605)
@@ -404,8 +427,9 @@ class WanTransformer3DFantasyModel(nn.Module):
 
         # ---- FFN (1B.py:687-691)
         t2 = ops.layernorm(h, shift=ch[3], scale=ch[4], mod_bs=6 * C, rows_per_batch=Ll)
-        hid = ops.gemm(t2, blk.ffn[0].weight, blk.ffn[0].bias, act=ops.ACT_GELU_TANH)
-        ops.gemm(hid, blk.ffn[2].weight, blk.ffn[2].bias, res=h, gate=ch[5], gate_ld=6 * C, rows_per_batch=Ll, out=h)
+        with ops.timed("ffn"):
+            hid = ops.gemm(t2, blk.ffn[0].weight, blk.ffn[0].bias, act=ops.ACT_GELU_TANH)
+            ops.gemm(hid, blk.ffn[2].weight, blk.ffn[2].bias, res=h, gate=ch[5], gate_ld=6 * C, rows_per_batch=Ll, out=h)
         return h
 
     def _audio_attention(self, q, kvv, a, st, Ll):

@@ -108,3 +108,29 @@ def test_rope_and_sinusoid(gold):
     out = O.rope_apply(q, [(2, 4, 6), (2, 4, 6)], fr)
     assert np.allclose(out.numpy(), gold["rope_apply"], atol=1e-6)
     assert torch.equal(out[:, 48:], q[:, 48:])                   # tokens beyond f*h*w are not rotated
+
+
+# ---------------------------------------------------------------------------------------------- Wan VAE decode
+@pytest.fixture(scope="module")
+def vae_gold(golden_dir):
+    return np.load(golden_dir / "vae_tiny.npz")
+
+
+def test_vae_decode_three_latent_frames(vae_gold):
+    """1 + 4 + 4 frames: first-chunk 'Rep' path, 1-frame caches growing to 2, both temporal upsamplers."""
+    from oracle import vae as V
+    sd = synth.vae_state_dict()
+    with torch.no_grad():
+        out = V.vae_decode(sd, synth.det_normal("vae_z", (1, 16, 3, 6, 8)))
+    assert out.shape == (1, 3, 9, 48, 64)
+    assert rel(out, vae_gold["z3_out"]) < 1e-4
+    assert out.abs().max() <= 1.0
+
+
+def test_vae_decode_single_frame_batch(vae_gold):
+    from oracle import vae as V
+    sd = synth.vae_state_dict()
+    with torch.no_grad():
+        out = V.vae_decode(sd, synth.det_normal("vae_z1", (2, 16, 1, 4, 6)))
+    assert out.shape == (2, 3, 1, 32, 48)
+    assert rel(out, vae_gold["z1_out"]) < 1e-4

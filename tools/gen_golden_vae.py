@@ -1,0 +1,42 @@
+"""Golden fixture of the Wan VAE decode from the REAL reference module (wan/models/wan_vae.py), see gen_golden.py."""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle.refstub import import_reference  # noqa: E402
+from stableavatar_b200 import synth  # noqa: E402
+
+
+def gen_vae():
+    _, _, vae = import_reference()
+    m = vae.AutoencoderKLWan().eval()
+    ref_sd = m.state_dict()
+    sd = synth.vae_state_dict()
+    dec_keys = {k: tuple(v.shape) for k, v in ref_sd.items() if k.startswith("model.decoder.") or k.startswith("model.conv2.")}
+    mine = {k: tuple(v) for k, v in synth.vae_decoder_param_shapes().items()}
+    assert dec_keys == mine, (set(dec_keys) ^ set(mine), [(k, dec_keys[k], mine[k]) for k in dec_keys if k in mine and dec_keys[k] != mine[k]])
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("model.encoder.") or k.startswith("model.conv1.") for k in missing)
+    res = {}
+    z = synth.det_normal("vae_z", (1, 16, 3, 6, 8))
+    with torch.no_grad():
+        out = m.decode(z).sample
+    res["z3_out"] = out.numpy()
+    z1 = synth.det_normal("vae_z1", (2, 16, 1, 4, 6))                # single latent frame (first-chunk 'Rep' path), batch 2
+    with torch.no_grad():
+        res["z1_out"] = m.decode(z1).sample.numpy()
+    res["config"] = np.array([m.config.latent_channels, m.config.temporal_compression_ratio, m.config.spacial_compression_ratio])
+    np.savez_compressed(ROOT / "tests" / "golden" / "vae_tiny.npz", **res)
+    print("wrote vae_tiny.npz", {k: v.shape for k, v in res.items()})
+
+
+if __name__ == "__main__":
+    torch.set_grad_enabled(False)
+    gen_vae()
