@@ -157,6 +157,43 @@ int sa_gather_rows_f32(const void* src, const void* idx, void* out, int32_t rows
 int sa_cfg_euler_step(const void* pred, const void* latents, void* out, void* noise_out, int64_t n, float audio_scale,
                       float text_scale, float dsigma, int32_t cfg, sa_stream_t stream);
 
+/* ---- Wan VAE decode (wan/models/wan_vae.py) --------------------------------------------------------------------
+ * Activations are channels-last bf16 [T, H, W, C] (the reference is NCTHW fp32; layout and compute dtype are internal
+ * to the decode, the boundary stays AutoencoderKLWan.decode's NCTHW fp32 in / out).
+ *
+ * sa_conv3d_cl: causal conv as an implicit GEMM on tcgen05 — CausalConv3d (wan_vae.py:20-39) incl. the 3x3x3 convs
+ * of ResidualBlock (:197-203), Decoder3d.conv1 / head (:394, 421-424), Resample's (3,1,1) time_conv and 3x3 Conv2d
+ * (:79-88). `in` holds Tout + KT - 1 frames: the KT - 1 leading ones are the causal cache (zeros before the first
+ * chunk), replacing the per-chunk clone/cat of :208-220; H/W 'same' zero padding is implicit.
+ *   w: bf16 [ceil16(Cout), KT*KH*KW*Cin], K index = ((kt*KH + kh)*KW + kw)*Cin + c; bias: f32 [Cout]; Cin % 32 == 0.
+ *   out_mode 0: out bf16 [Tout,H,W,Cout] = acc + bias (+ res, same layout: the x + h of :223)
+ *   out_mode 1: Cout = 2C; channel n of frame t goes to frame 2t + n/C, channel n%C of bf16 [2*Tout,H,W,C] (:137-140)
+ *   out_mode 2: out f32 planar [Cout, out_T_total, H, W] at frame out_t0 + t, clamped to [-1, 1] (:668)
+ */
+typedef struct {
+  const void* in;
+  const void* w;
+  const void* bias;
+  const void* res;
+  void* out;
+  int32_t Tout, H, W, Cin, Cout, KT, KH, KW;
+  int32_t out_mode, out_T_total, out_t0;
+} sa_conv_args;
+int sa_conv3d_cl(const sa_conv_args* args, sa_stream_t stream);
+
+/* out = x / max(||x||_2, 1e-12) * sqrt(C) * gamma per position, then SiLU if silu != 0: RMS_norm (wan_vae.py:42-57) +
+ * nn.SiLU of ResidualBlock / head / AttentionBlock.norm. x/out bf16 [P, C], gamma f32 [C]. */
+int sa_vae_rmsnorm_silu(const void* x, const void* gamma, void* out, int64_t P, int32_t C, int32_t silu, sa_stream_t stream);
+/* out[t, y, x, :] = in[t, y/2, x/2, :]: Upsample(scale 2, nearest-exact) of Resample (wan_vae.py:60-66, 79-84). */
+int sa_vae_upsample2x(const void* in, void* out, int32_t T, int32_t H, int32_t W, int32_t C, sa_stream_t stream);
+/* out[r, :] = bf16(softmax(in[r, :] * scale)), in f32: the softmax of AttentionBlock's SDPA (wan_vae.py:254-259). */
+int sa_softmax_rows(const void* in, void* out, int32_t rows, int32_t n, int64_t ld_in, int64_t ld_out, float scale,
+                    sa_stream_t stream);
+/* x = conv2(z / (1/std) + mean): latent de-normalisation + 1x1x1 conv (wan_vae.py:552-559). z f32 [Cz, P] planar ->
+ * bf16 [P, Cpad] channels-last, channels >= Cz zero. wc f32 [Cz, Cz], bc/mean/stdv f32 [Cz]. */
+int sa_vae_latent_in(const void* z, const void* wc, const void* bc, const void* mean, const void* stdv, void* out,
+                     int32_t Cz, int64_t P, int32_t Cpad, sa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

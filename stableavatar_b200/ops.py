@@ -216,3 +216,74 @@ def cfg_euler_step(pred, latents, dsigma, audio_scale=0.0, text_scale=0.0, cfg=T
                                       C.c_float(audio_scale), C.c_float(text_scale), C.c_float(dsigma), int(cfg),
                                       L.stream_ptr()), "sa_cfg_euler_step")
     return out
+
+
+# ---------------------------------------------------------------------------------------------- Wan VAE ops
+class ConvArgs(C.Structure):
+    _fields_ = [("inp", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("out", C.c_void_p),
+                ("Tout", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+                ("KT", C.c_int32), ("KH", C.c_int32), ("KW", C.c_int32),
+                ("out_mode", C.c_int32), ("out_T_total", C.c_int32), ("out_t0", C.c_int32)]
+
+
+def conv3d_cl(x, w, bias, *, cout, k, out, res=None, out_mode=0, out_T_total=0, out_t0=0):
+    """Causal conv on channels-last bf16 x [Tout + KT - 1, H, W, Cin] (leading frames = cache) — sa_conv3d_cl."""
+    _need_cuda(x, w)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w.dtype == torch.bfloat16 and w.is_contiguous()
+    assert bias.dtype == torch.float32 and out.is_contiguous() and (res is None or (res.is_contiguous() and res.dtype == torch.bfloat16))
+    Tin, H, W, Cin = x.shape
+    a = ConvArgs(inp=x.data_ptr(), w=w.data_ptr(), bias=bias.data_ptr(), res=L.ptr(res), out=out.data_ptr(),
+                 Tout=Tin - k[0] + 1, H=H, W=W, Cin=Cin, Cout=cout, KT=k[0], KH=k[1], KW=k[2], out_mode=out_mode,
+                 out_T_total=out_T_total, out_t0=out_t0)
+    L.check(L.lib().sa_conv3d_cl(C.byref(a), L.stream_ptr()), "sa_conv3d_cl")
+    return out
+
+
+def vae_rmsnorm_silu(x, gamma, out, silu=True):
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and out.is_contiguous() and gamma.dtype == torch.float32
+    Cc = x.shape[-1]
+    L.check(L.lib().sa_vae_rmsnorm_silu(C.c_void_p(x.data_ptr()), C.c_void_p(gamma.data_ptr()), C.c_void_p(out.data_ptr()),
+                                        C.c_int64(x.numel() // Cc), Cc, int(silu), L.stream_ptr()), "sa_vae_rmsnorm_silu")
+    return out
+
+
+def vae_upsample2x(x, out):
+    _need_cuda(x)
+    T, H, W, Cc = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and out.shape == (T, 2 * H, 2 * W, Cc)
+    L.check(L.lib().sa_vae_upsample2x(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), T, H, W, Cc, L.stream_ptr()),
+            "sa_vae_upsample2x")
+    return out
+
+
+def softmax_rows(s, scale):
+    _need_cuda(s)
+    assert s.dtype == torch.float32 and s.dim() == 2 and s.stride(1) == 1
+    out = torch.empty(s.shape, device=s.device, dtype=torch.bfloat16)
+    L.check(L.lib().sa_softmax_rows(C.c_void_p(s.data_ptr()), C.c_void_p(out.data_ptr()), s.shape[0], s.shape[1],
+                                    C.c_int64(s.stride(0)), C.c_int64(out.stride(0)), C.c_float(scale), L.stream_ptr()),
+            "sa_softmax_rows")
+    return out
+
+
+def softmax_rows_into(s, out, scale):
+    """out[r, :] = bf16(softmax(s[r, :] * scale)) for row-strided 2-D views."""
+    _need_cuda(s, out)
+    assert s.dtype == torch.float32 and out.dtype == torch.bfloat16 and s.shape == out.shape and s.stride(1) == out.stride(1) == 1
+    L.check(L.lib().sa_softmax_rows(C.c_void_p(s.data_ptr()), C.c_void_p(out.data_ptr()), s.shape[0], s.shape[1],
+                                    C.c_int64(s.stride(0)), C.c_int64(out.stride(0)), C.c_float(scale), L.stream_ptr()),
+            "sa_softmax_rows")
+    return out
+
+
+def vae_latent_in(z, wc, bc, mean, std, cpad):
+    _need_cuda(z)
+    Cz = z.shape[0]
+    P = z.numel() // Cz
+    assert z.dtype == torch.float32 and z.is_contiguous()
+    out = torch.empty(*z.shape[1:], cpad, device=z.device, dtype=torch.bfloat16)
+    L.check(L.lib().sa_vae_latent_in(C.c_void_p(z.data_ptr()), C.c_void_p(wc.data_ptr()), C.c_void_p(bc.data_ptr()),
+                                     C.c_void_p(mean.data_ptr()), C.c_void_p(std.data_ptr()), C.c_void_p(out.data_ptr()),
+                                     Cz, C.c_int64(P), cpad, L.stream_ptr()), "sa_vae_latent_in")
+    return out

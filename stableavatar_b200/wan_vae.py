@@ -1,0 +1,257 @@
+"""Wan causal-3D VAE decode on hand-written sm_100a kernels.
+
+Drop-in for the decode side of `AutoencoderKLWan` (wan/models/wan_vae.py:619-704): same constructor arguments,
+`.config.{latent_channels, temporal_compression_ratio, spacial_compression_ratio}`, the reference's state-dict key
+names (`model.decoder...`, `model.conv2...`; encoder keys are accepted and ignored), and
+`decode(z, return_dict=True) -> DecoderOutput(.sample)` with z [B,16,T,h,w] -> [B,3,1+4(T-1),8h,8w] fp32 in [-1,1].
+
+Internals are B200-first rather than a transcription of Decoder3d.forward (:426-475): activations are channels-last
+bf16, every 3x3x3 causal conv is an implicit GEMM on tcgen05 fed by TMA (ops.conv3d_cl), and the 33-entry feature cache
+(:549-574 — `x[:, :, -2:].clone()` + `torch.cat` per conv per chunk) becomes one persistent ring buffer per conv whose
+two leading frames are the cache: the producer of a conv's input writes straight behind them. Chunking follows the
+reference exactly (one latent frame per chunk, chunk 0 skips the temporal upsamplers and yields a single frame).
+
+`encode` is outside the hot path and is not implemented here: pass the reference's VAE, or
+pre-encoded conditioning latents, to the pipeline for that one call.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .synth import vae_decoder_layout, vae_decoder_param_shapes
+
+LATENT_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508, 0.4134, -0.0715, 0.5517, -0.3632,
+               -0.1922, -0.9497, 0.2503, -0.2921]
+LATENT_STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743, 3.2687, 2.1526, 2.8652, 1.5579, 1.6382,
+              1.1253, 2.8251, 1.9160]
+
+
+class DecoderOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+
+def _build_param_tree(root: nn.Module, shapes: dict):
+    for name, shape in shapes.items():
+        mod = root
+        *path, leaf = name.split(".")
+        for part in path:
+            if not hasattr(mod, part):
+                mod.add_module(part, nn.Module())
+            mod = getattr(mod, part)
+        mod.register_parameter(leaf, nn.Parameter(torch.empty(*shape), requires_grad=False))
+
+
+class _Conv:
+    """One causal conv with its persistent input ring buffer [2 + Tmax, H, W, Cin] (two leading cache frames)."""
+
+    def __init__(self, weight, bias, dev):
+        if weight.dim() == 4:
+            weight = weight.unsqueeze(2)
+        cout, cin, kt, kh, kw = weight.shape
+        self.cout, self.cin, self.k = cout, (cin + 31) // 32 * 32, (kt, kh, kw)
+        cout_pad = (cout + 15) // 16 * 16
+        w = torch.zeros(cout_pad, kt, kh, kw, self.cin, device=dev, dtype=torch.float32)
+        w[:cout, ..., :cin] = weight.to(dev, torch.float32).permute(0, 2, 3, 4, 1)
+        self.w = w.reshape(cout_pad, -1).to(torch.bfloat16).contiguous()
+        self.bias = bias.to(dev, torch.float32).contiguous()
+        self.buf = None
+
+    def alloc(self, tmax, H, W, dev):
+        lead = self.k[0] - 1
+        if self.buf is None or self.buf.shape != (lead + tmax, H, W, self.cin):
+            self.buf = torch.zeros(lead + tmax, H, W, self.cin, device=dev, dtype=torch.bfloat16)
+        else:
+            self.buf[:lead].zero_()
+        return self
+
+    def slot(self, tc):
+        """Where the producer writes this chunk's `tc` input frames."""
+        lead = self.k[0] - 1
+        return self.buf[lead:lead + tc]
+
+    def run(self, tc, out, res=None, keep_cache=True, **kw):
+        lead = self.k[0] - 1
+        ops.conv3d_cl(self.buf[:lead + tc], self.w, self.bias, cout=self.cout, k=self.k, out=out, res=res, **kw)
+        if keep_cache and lead:                      # new cache = last two frames of [old cache, x]  (wan_vae.py:208-220)
+            for j in range(lead):
+                self.buf[j].copy_(self.buf[tc + j])
+        return out
+
+
+class AutoencoderKLWan(nn.Module):
+    def __init__(self, latent_channels=16, temporal_compression_ratio=4, spacial_compression_ratio=8):
+        super().__init__()
+        self.config = SimpleNamespace(latent_channels=latent_channels, temporal_compression_ratio=temporal_compression_ratio,
+                                      spacial_compression_ratio=spacial_compression_ratio)
+        self.dims, self.mods = vae_decoder_layout()
+        _build_param_tree(self, vae_decoder_param_shapes(z_dim=latent_channels))
+        self.mean = torch.tensor(LATENT_MEAN, dtype=torch.float32)
+        self.std = torch.tensor(LATENT_STD, dtype=torch.float32)
+        self.scale = [self.mean, 1.0 / self.std]
+        self._prep = None
+
+    @property
+    def dtype(self):
+        return torch.float32          # the boundary dtype of the reference VAE (inference.py:471-474)
+
+    @property
+    def device(self):
+        return self.model.conv2.weight.device
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        self._prep = None
+        own = set(self.state_dict().keys())
+        kept = {k: v for k, v in state_dict.items() if k in own}
+        extra = [k for k in state_dict if k not in own and not (k.startswith("model.encoder.") or k.startswith("model.conv1."))]
+        if strict and extra:
+            raise RuntimeError(f"unexpected keys: {extra[:5]}")
+        return super().load_state_dict(kept, strict=strict, assign=assign)
+
+    def _apply(self, fn, *a, **k):
+        self._prep = None
+        return super()._apply(fn, *a, **k)
+
+    def encode(self, x, return_dict=True):
+        raise NotImplementedError("AutoencoderKLWan (B200): encode is outside the accelerated hot path (SURVEY.md §8f); "
+                                  "use the reference VAE for the one conditioning encode or pass latents directly")
+
+    # ------------------------------------------------------------------ one-time operand preparation
+    def _prepare(self):
+        if self._prep is not None:
+            return self._prep
+        sd = {k: v for k, v in self.state_dict().items()}
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("AutoencoderKLWan (B200): parameters must live on a CUDA device; there is no CPU fallback")
+        P = "model.decoder."
+        conv = lambda n: _Conv(sd[n + ".weight"], sd[n + ".bias"], dev)  # noqa: E731
+        f32 = lambda n: sd[n].to(dev, torch.float32).reshape(-1).contiguous()  # noqa: E731
+        bf = lambda t: t.to(dev, torch.bfloat16).contiguous()  # noqa: E731
+
+        def res(pre, cin, cout):
+            d = dict(g0=f32(pre + "residual.0.gamma"), c0=conv(pre + "residual.2"), g1=f32(pre + "residual.3.gamma"),
+                     c1=conv(pre + "residual.6"), cin=cin, cout=cout)
+            if cin != cout:
+                d["w_sc"] = bf(sd[pre + "shortcut.weight"].reshape(cout, cin))
+                d["b_sc"] = bf(sd[pre + "shortcut.bias"])
+            return d
+
+        c = self.dims[0]
+        wqkv, bqkv = sd[P + "middle.1.to_qkv.weight"].reshape(3 * c, c), sd[P + "middle.1.to_qkv.bias"]
+        attn = dict(g=f32(P + "middle.1.norm.gamma"), w_qk=bf(wqkv[:2 * c]), b_qk=bf(bqkv[:2 * c]), w_v=bf(wqkv[2 * c:]),
+                    b_v=bf(bqkv[2 * c:]), w_o=bf(sd[P + "middle.1.proj.weight"].reshape(c, c)), b_o=bf(sd[P + "middle.1.proj.bias"]))
+        ups = []
+        for i, m in enumerate(self.mods):
+            q = f"{P}upsamples.{i}."
+            if m[0] == "res":
+                ups.append(("res", res(q, m[1], m[2])))
+            else:
+                d = dict(c=m[1], conv=conv(q + "resample.1"))
+                if m[0] == "up3d":
+                    d["tconv"] = conv(q + "time_conv")
+                ups.append((m[0], d))
+        self._prep = dict(conv1=conv(P + "conv1"), mid0=res(P + "middle.0.", c, c), attn=attn, mid2=res(P + "middle.2.", c, c),
+                          ups=ups, head_g=f32(P + "head.0.gamma"), head=conv(P + "head.2"),
+                          wc=sd["model.conv2.weight"].to(dev, torch.float32).reshape(16, 16).contiguous(),
+                          bc=sd["model.conv2.bias"].to(dev, torch.float32).contiguous(),
+                          mean=self.mean.to(dev), std=self.std.to(dev))
+        return self._prep
+
+    # ------------------------------------------------------------------ decode
+    def _res_block(self, d, a, tc):
+        """ResidualBlock (wan_vae.py:205-223): x + conv(silu(norm(conv(silu(norm(x)))))) with an optional 1x1x1 shortcut."""
+        T, H, W, _ = a.shape
+        dev = a.device
+        if "w_sc" in d:
+            h = ops.gemm(a.view(-1, d["cin"]), d["w_sc"], d["b_sc"]).view(T, H, W, d["cout"])
+        else:
+            h = a
+        ops.vae_rmsnorm_silu(a, d["g0"], d["c0"].slot(tc))
+        b = d["c0"].run(tc, torch.empty(T, H, W, d["cout"], device=dev, dtype=torch.bfloat16))
+        ops.vae_rmsnorm_silu(b, d["g1"], d["c1"].slot(tc))
+        return d["c1"].run(tc, torch.empty(T, H, W, d["cout"], device=dev, dtype=torch.bfloat16), res=h)
+
+    def _attention(self, d, a):
+        """AttentionBlock (wan_vae.py:243-265): per frame, one head of width C over H*W positions."""
+        T, H, W, C = a.shape
+        P = H * W
+        ldp = (P + 7) // 8 * 8
+        out = torch.empty_like(a)
+        for t in range(T):
+            x = a[t].view(P, C)
+            xn = ops.vae_rmsnorm_silu(x, d["g"], torch.empty_like(x), silu=False)
+            qk = ops.gemm(xn, d["w_qk"], d["b_qk"])                                       # [P, 2C]
+            vt = torch.zeros(C, ldp, device=a.device, dtype=torch.bfloat16)
+            ops.gemm(d["w_v"], xn, out=vt[:, :P])                                         # V^T [C, P] (bias folded below)
+            s = torch.empty(P, ldp, device=a.device, dtype=torch.float32)
+            ops.gemm(qk[:, :C], qk[:, C:], out=s[:, :P], round_y=False)                   # q k^T in fp32
+            p = torch.zeros(P, ldp, device=a.device, dtype=torch.bfloat16)
+            ops.softmax_rows_into(s[:, :P], p[:, :P], C ** -0.5)
+            o = ops.gemm(p, vt, d["b_v"])                                                 # softmax rows sum to 1: P(V + b) = PV + b
+            ops.gemm(o, d["w_o"], d["b_o"], res=x, out=out[t].view(P, C))
+        return out
+
+    @torch.no_grad()
+    def _decode_one(self, z, video):
+        """z [16, T, h, w] fp32 (one sample) -> video [3, 1 + 4 (T-1), 8h, 8w] fp32, AutoencoderKLWan_.decode :549-574."""
+        p = self._prepare()
+        dev = z.device
+        _, T, h, w = z.shape
+        bf = torch.bfloat16
+        x_all = ops.vae_latent_in(z.contiguous(), p["wc"], p["bc"], p["mean"], p["std"], 32)          # [T, h, w, 32]
+        # ring buffers sized for the steady-state chunk (1 / 2 / 4 frames per stage)
+        p["conv1"].alloc(1, h, w, dev)
+        for d in (p["mid0"], p["mid2"]):
+            d["c0"].alloc(1, h, w, dev), d["c1"].alloc(1, h, w, dev)
+        tmax, H, W = 1, h, w
+        for kind, d in p["ups"]:
+            if kind == "res":
+                d["c0"].alloc(tmax, H, W, dev), d["c1"].alloc(tmax, H, W, dev)
+            else:
+                if kind == "up3d":
+                    d["tconv"].alloc(tmax, H, W, dev)
+                    tmax *= 2
+                H, W = 2 * H, 2 * W
+                d["conv"].alloc(tmax, H, W, dev)
+        p["head"].alloc(tmax, H, W, dev)
+        n_out = video.shape[1]
+        t_out = 0
+        for i in range(T):
+            tc = 1
+            p["conv1"].slot(1).copy_(x_all[i:i + 1])
+            a = p["conv1"].run(1, torch.empty(1, h, w, self.dims[0], device=dev, dtype=bf))
+            a = self._res_block(p["mid0"], a, 1)
+            a = self._attention(p["attn"], a)
+            a = self._res_block(p["mid2"], a, 1)
+            for kind, d in p["ups"]:
+                if kind == "res":
+                    a = self._res_block(d, a, tc)
+                    continue
+                Tc, Hc, Wc, C = a.shape
+                if kind == "up3d" and i > 0:                      # chunk 0: 'Rep' — no temporal upsampling (wan_vae.py:108-112)
+                    d["tconv"].slot(tc).copy_(a)
+                    a = d["tconv"].run(tc, torch.empty(2 * tc, Hc, Wc, C, device=dev, dtype=bf), out_mode=1)
+                    tc *= 2
+                ops.vae_upsample2x(a, d["conv"].slot(tc))
+                a = d["conv"].run(tc, torch.empty(tc, 2 * Hc, 2 * Wc, C // 2, device=dev, dtype=bf))
+            ops.vae_rmsnorm_silu(a, p["head_g"], p["head"].slot(tc))
+            p["head"].run(tc, video, out_mode=2, out_T_total=n_out, out_t0=t_out)
+            t_out += tc
+        assert t_out == n_out, (t_out, n_out)
+
+    @torch.no_grad()
+    def decode(self, z, return_dict=True):
+        dev = self.device
+        z = z.to(dev, torch.float32)
+        B, _, T, h, w = z.shape
+        video = torch.empty(B, 3, 1 + 4 * (T - 1), 8 * h, 8 * w, device=dev, dtype=torch.float32)
+        for b in range(B):
+            self._decode_one(z[b], video[b])
+        if not return_dict:
+            return (video,)
+        return DecoderOutput(sample=video)

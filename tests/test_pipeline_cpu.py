@@ -1,0 +1,56 @@
+"""CPU tests of the host-side loop logic (no GPU): window schedule, overlap weights and scheduler tables of
+stableavatar_b200/pipeline.py + scheduler.py against the oracle restatement of the reference loop."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline as OP
+from stableavatar_b200.pipeline import overlap_weights, window_schedule
+from stableavatar_b200.scheduler import FlowMatchEulerDiscreteScheduler
+
+
+def oracle_windows(infer_length, fpb, overlap):
+    seen = []
+    lat = torch.zeros(1, 1, infer_length, 1, 1)
+
+    def fn(latents, t, ws, we, is_last):
+        seen.append((ws, we, is_last))
+        return torch.zeros(3, *latents.shape[1:])
+    OP.denoise_loop(fn, lat, 1, (fpb - 1) * 4 + 1, overlap)
+    return seen
+
+
+@pytest.mark.parametrize("infer_length,fpb,overlap", [(42, 21, 15), (21, 21, 5), (30, 21, 5), (64, 21, 10), (43, 21, 15), (22, 21, 3)])
+def test_window_schedule_matches_reference_loop(infer_length, fpb, overlap):
+    want = oracle_windows(infer_length, fpb, overlap)
+    got = window_schedule(infer_length, fpb, overlap)
+    assert [(a, b) for a, b, _ in got] == [(a, b) for a, b, _ in want]
+    assert got[-1][1] == infer_length
+
+
+def test_appendix_c_example():
+    # 42 latent frames, 21 per window, overlap 15
+    assert [(a, b) for a, b, _ in window_schedule(42, 21, 15)] == [(0, 21), (6, 27), (12, 33), (18, 39), (24, 42)]
+
+
+def test_no_window_when_clip_shorter_than_a_window():
+    assert window_schedule(10, 21, 5) == []
+
+
+@pytest.mark.parametrize("n", [10, 50])
+def test_sigma_table(n):
+    s = FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=5.0)
+    s.set_timesteps(n, device="cpu", mu=1)
+    sig, ts = OP.flow_match_sigmas(n)
+    assert torch.equal(s.sigmas, sig) and torch.equal(s.timesteps.cpu(), ts)
+    assert s.sigmas[-1] == 0 and s.sigmas[0] > 0.99 and (s.sigmas[:-1] > s.sigmas[1:]).all()
+    for i in (0, n // 2, n - 1):
+        assert s.index_for_timestep(s.timesteps[i]) == i
+        assert s.dsigma_at(i) == float(sig[i + 1] - sig[i])
+
+
+def test_overlap_weights():
+    w = overlap_weights(5, "uniform", "cpu", torch.float32).flatten()
+    assert torch.allclose(w, torch.tensor([0.0, 0.25, 0.5, 0.75, 1.0]))
+    w = overlap_weights(5, "log", "cpu", torch.float32).flatten()
+    assert w[0] == 0 and abs(w[-1].item() - 1) < 1e-6 and (w[1:] > w[:-1]).all()
