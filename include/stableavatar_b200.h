@@ -152,7 +152,8 @@ int sa_gather_rows_f32(const void* src, const void* idx, void* out, int32_t rows
 /* ---- scheduler step ------------------------------------------------------------------------------------------
  * cfg != 0: pred = [uncond, drop_audio, cond] (3 x n bf16); noise = uncond + audio_scale*(drop_audio - uncond) +
  * text_scale*(cond - drop_audio), each op rounded to bf16 (wan/pipeline/wan_inference_long_pipeline.py:751-753).
- * out = bf16(float(latents) + dsigma * float(noise)): FlowMatchEulerDiscreteScheduler.step of diffusers 0.30.1
+ * out = bf16(float(latents) + bf16(dsigma * noise)): FlowMatchEulerDiscreteScheduler.step of diffusers 0.30.1 (the
+ * 0-dim fp32 (sigma_next - sigma) times the bf16 prediction is a bf16 tensor under torch type promotion)
  * (pipe.py:754). noise_out (optional) receives the combined prediction. */
 int sa_cfg_euler_step(const void* pred, const void* latents, void* out, void* noise_out, int64_t n, float audio_scale,
                       float text_scale, float dsigma, int32_t cfg, sa_stream_t stream);

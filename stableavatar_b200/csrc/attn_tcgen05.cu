@@ -35,6 +35,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = (2 + 2 * KV_STAGES) * TILE_BYTES + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kDefaultPolyPairs = 2;       // of every 8 column pairs, how many use the FMA-pipe exp2 (SA_ATTN_POLY overrides)
+constexpr int kDefaultImpl = 2;            // 2: this file; 4: decoupled kernel of attn_v4_tcgen05.cu (SA_ATTN_IMPL overrides)
 
 struct Params {
   __nv_bfloat16* out;
@@ -101,7 +102,7 @@ flash_attn_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: single active lane is known to ptxas -> no R2UR waterfall per UTCHMMA / UTMALDG
       auto load_tile = [&](uint8_t* dst, const CUtensorMap* m, uint64_t* bar, int row0) {
         mbar_arrive_expect_tx(bar, TILE_BYTES);
         tma_load_4d(dst, m, bar, 0, row0, head, b);
@@ -122,7 +123,7 @@ flash_attn_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: single active lane is known to ptxas -> no R2UR waterfall per UTCHMMA / UTMALDG
       const uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);  // A = Q (K-major), B = K (K-major)
       const uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);    // A = P (TMEM),   B = V (MN-major: d contiguous)
       auto issue_S = [&](int i, int ks) {
@@ -357,6 +358,8 @@ flash_attn_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 }  // namespace attn
 }  // namespace sa
 
+int sa_flash_attn_d128_v4(const sa_attn_args* a, int poly, cudaStream_t stream);  // attn_v4_tcgen05.cu
+
 extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
   using namespace sa;
   using namespace sa::attn;
@@ -371,6 +374,15 @@ extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
     set_error("sa_flash_attn_d128: strides must be multiples of 8 elements");
     return SA_ERR_BAD_ARG;
   }
+  static int impl = -1, poly_env = -1;
+  if (impl < 0) {
+    const char* e1 = getenv("SA_ATTN_IMPL");
+    impl = e1 ? atoi(e1) : kDefaultImpl;
+    const char* e2 = getenv("SA_ATTN_POLY");
+    poly_env = e2 ? atoi(e2) : kDefaultPolyPairs;
+    if (poly_env < 0 || poly_env > 4) poly_env = kDefaultPolyPairs;
+  }
+  if (impl == 4) return sa_flash_attn_d128_v4(a, poly_env, stream);
   CUtensorMap tq, tk, tv;
   auto mk = [&](CUtensorMap* m, const void* base, int len, long long ls, long long bs) {
     uint64_t dims[4] = {(uint64_t)D, (uint64_t)len, (uint64_t)a->heads, (uint64_t)a->batch};

@@ -98,7 +98,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: single active lane is known to ptxas -> no R2UR waterfall per UTCHMMA / UTMALDG
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int nt, t, h0, w0;
@@ -121,7 +121,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: single active lane is known to ptxas -> no R2UR waterfall per UTCHMMA / UTMALDG
       const uint32_t idesc = umma_idesc_bf16(BM, p.bn, 0, 0);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {

@@ -168,7 +168,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync (not lane == 0): ptxas then knows a single lane is active and feeds the uniform
+                        // operands of UTMALDG / UTCHMMA with plain R2UR instead of a per-instruction waterfall loop
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.tiles_n) * BM;
@@ -186,7 +187,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {

@@ -127,7 +127,7 @@ __global__ void gather_rows_kernel(const float* src, const int* idx, float* out,
 
 // ------------------------------------------------------------------------------------------------ CFG + Euler
 // noise = uncond + a*(drop_audio - uncond) + t*(cond - drop_audio)   every op a bf16 tensor op (pipe.py:752-753)
-// latents = bf16(float(latents) + dsigma * float(noise))             (diffusers FlowMatchEulerDiscreteScheduler.step)
+// latents = bf16(float(latents) + bf16(dsigma * noise))             (diffusers FlowMatchEulerDiscreteScheduler.step)
 __global__ void cfg_euler_kernel(const __nv_bfloat16* pred, const __nv_bfloat16* lat, __nv_bfloat16* out,
                                  __nv_bfloat16* noise_out, long long n, float audio_scale, float text_scale,
                                  float dsigma, int cfg) {
@@ -143,7 +143,10 @@ __global__ void cfg_euler_kernel(const __nv_bfloat16* pred, const __nv_bfloat16*
       np = __bfloat162float(pred[i]);
     }
     if (noise_out) noise_out[i] = __float2bfloat16_rn(np);
-    out[i] = __float2bfloat16_rn(__bfloat162float(lat[i]) + dsigma * np);
+    // (sigma_next - sigma) is a 0-dim fp32 tensor: its product with the bf16 prediction is a bf16 tensor (type
+    // promotion ignores 0-dim operands of the same category); the add with the fp32 sample is fp32; no FMA contraction.
+    const float step = bf16_round(__fmul_rn(dsigma, np));
+    out[i] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(lat[i]), step));
   }
 }
 
