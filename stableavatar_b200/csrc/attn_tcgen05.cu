@@ -34,8 +34,8 @@ constexpr int NUM_THREADS = 320;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = (2 + 2 * KV_STAGES) * TILE_BYTES + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-constexpr int kDefaultPolyPairs = 2;       // of every 8 column pairs, how many use the FMA-pipe exp2 (SA_ATTN_POLY overrides)
-constexpr int kDefaultImpl = 2;            // 2: this file; 4: decoupled kernel of attn_v4_tcgen05.cu (SA_ATTN_IMPL overrides)
+constexpr int kDefaultPolyPairs = 0;       // of every 8 column pairs, how many use the FMA-pipe exp2 (SA_ATTN_POLY overrides)
+constexpr int kDefaultImpl = 4;            // 2: this file; 4: decoupled kernel of attn_v4_tcgen05.cu (SA_ATTN_IMPL overrides)
 
 struct Params {
   __nv_bfloat16* out;

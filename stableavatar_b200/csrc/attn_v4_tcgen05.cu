@@ -204,7 +204,7 @@ flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
     const float c = p.scale_log2;
     const uint64_t c2 = pack_f32x2(c, c);
     float m_ref = 0.f;
-    uint64_t lsum2 = pack_f32x2(0.f, 0.f);
+    uint64_t lsum2 = pack_f32x2(0.f, 0.f), lsum2b = pack_f32x2(0.f, 0.f);  // two independent row-sum chains
 
     auto step = [&](int u, auto mask_tag) {
       constexpr bool MASK = decltype(mask_tag)::value;
@@ -266,6 +266,8 @@ flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
         float l_lo, l_hi;
         unpack_f32x2(lsum2, l_lo, l_hi);
         lsum2 = pack_f32x2(l_lo * alpha, l_hi * alpha);
+        unpack_f32x2(lsum2b, l_lo, l_hi);
+        lsum2b = pack_f32x2(l_lo * alpha, l_hi * alpha);
       }
       const float nmc = -m_ref * c;
       const uint64_t nmc2 = pack_f32x2(nmc, nmc);
@@ -304,7 +306,8 @@ flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
             p2 = pack_f32x2(p0, p1);
             pk[t4] = pack_bf16x2(p0, p1);
           }
-          lsum2 = add_f32x2(lsum2, p2);
+          if (t4 & 1) lsum2b = add_f32x2(lsum2b, p2);
+          else lsum2 = add_f32x2(lsum2, p2);
         }
         *reinterpret_cast<uint4*>(p_row + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
@@ -323,6 +326,7 @@ flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
     mbar_wait(&o_final[i], 0, 0x4500 | i);
     tc_fence_after();
     float l_lo, l_hi;
+    lsum2 = add_f32x2(lsum2, lsum2b);
     unpack_f32x2(lsum2, l_lo, l_hi);
     const float inv_l = 1.0f / (l_lo + l_hi);
     __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)row * p.o_ls + head * D;
