@@ -1,0 +1,28 @@
+"""Full-size Wan VAE decode timing on one B200: z [1,16,T,60,104] -> [1,3,1+4(T-1),480,832] (BASELINE config 4)."""
+import sys
+import time
+import torch
+sys.path.insert(0, ".")
+from stableavatar_b200 import synth, _lib
+from stableavatar_b200.wan_vae import AutoencoderKLWan
+
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 21
+h, w = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (60, 104)
+vae = AutoencoderKLWan()
+vae.load_state_dict(synth.vae_state_dict(), strict=True)
+vae = vae.to("cuda")
+z = synth.det_normal("vae_zfull", (1, 16, T, h, w)).cuda()
+out = vae.decode(z).sample          # warm-up (allocations, attribute setup)
+torch.cuda.synchronize()
+_lib.launch_count = 0
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter()
+e0.record()
+out = vae.decode(z).sample
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1)
+flop = (4.29 + (T - 1) * 13.49 + T * 0.06) * 1e12 * (h * w) / (60 * 104)
+print(f"vae decode T={T} {h}x{w}: {ms:.1f} ms (wall {1e3 * (time.perf_counter() - t0):.1f} ms), {flop / ms / 1e9:.1f} TFLOP/s, "
+      f"{_lib.launch_count} kernel launches, out {tuple(out.shape)} finite={bool(torch.isfinite(out).all())} "
+      f"mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
