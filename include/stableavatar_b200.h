@@ -154,9 +154,11 @@ int sa_gather_rows_f32(const void* src, const void* idx, void* out, int32_t rows
  * text_scale*(cond - drop_audio), each op rounded to bf16 (wan/pipeline/wan_inference_long_pipeline.py:751-753).
  * out = bf16(float(latents) + bf16(dsigma * noise)): FlowMatchEulerDiscreteScheduler.step of diffusers 0.30.1 (the
  * 0-dim fp32 (sigma_next - sigma) times the bf16 prediction is a bf16 tensor under torch type promotion)
- * (pipe.py:754). noise_out (optional) receives the combined prediction. */
+ * (pipe.py:754). noise_out (optional) receives the combined prediction.
+ * dsigma_dev (optional, device float): when non-NULL it replaces dsigma, so a captured CUDA graph of the step can be
+ * replayed with a new schedule value. */
 int sa_cfg_euler_step(const void* pred, const void* latents, void* out, void* noise_out, int64_t n, float audio_scale,
-                      float text_scale, float dsigma, int32_t cfg, sa_stream_t stream);
+                      float text_scale, float dsigma, const void* dsigma_dev, int32_t cfg, sa_stream_t stream);
 
 /* ---- Wan VAE decode (wan/models/wan_vae.py) --------------------------------------------------------------------
  * Activations are channels-last bf16 [T, H, W, C] (the reference is NCTHW fp32; layout and compute dtype are internal

@@ -61,8 +61,11 @@ flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
   uint64_t* kv_empty = bars + STAGES;       // [STAGES]
   uint64_t* s_full = bars + 2 * STAGES;     // [2]  S_i(u) complete in TMEM
   uint64_t* s_cons = s_full + 2;            // [2]  softmax i has S_i(u) in registers
-  uint64_t* p_full = s_cons + 2;            // [2]  P_i(u) in shared memory (and O_i rescaled if needed)
-  uint64_t* pv_done = p_full + 2;           // [2]  one completion per PV_i(u)
+  uint64_t* p_full = s_cons + 2;            // [2 tiles][2 P buffers]  P_i(u) in shared memory (and O_i rescaled if needed).
+                                            // One barrier per P buffer: a softmax warpgroup may finish steps u and u+1
+                                            // before the MMA warp (held up by the other tile) consumes P_i(u); with a
+                                            // single barrier those two completions would alias in the phase parity.
+  uint64_t* pv_done = p_full + 4;           // [2]  one completion per PV_i(u)
   uint64_t* o_final = pv_done + 2;          // [2]
   uint64_t* q_ready = o_final + 2;          // [1]  Q tiles stored in TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
@@ -87,10 +90,10 @@ flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
         mbar_init(&s_cons[i], 4);
-        mbar_init(&p_full[i], 4);
         mbar_init(&pv_done[i], 1);
         mbar_init(&o_final[i], 1);
       }
+      for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
       mbar_init(q_ready, 8);
       fence_barrier_init();
     }
@@ -161,7 +164,7 @@ flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          mbar_wait(&p_full[i], u & 1, 0x4340 | i);
+          mbar_wait(&p_full[i * 2 + (u & 1)], (u >> 1) & 1, 0x4340 | (i * 2 + (u & 1)));
           tc_fence_after();
           issue_PV(i, u);
           if (last) umma_commit(&o_final[i]);
@@ -272,6 +275,41 @@ flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
       const float nmc = -m_ref * c;
       const uint64_t nmc2 = pack_f32x2(nmc, nmc);
       uint8_t* p_row = p_row0 + (u & 1) * P_BYTES;
+      if constexpr (kPolyPairs == 0) {
+        // Staged so that no instruction waits on its predecessor: (A) 32 independent packed scales, (B) 64 MUFU.EX2
+        // back to back (the XU pipe, 8 cycles per warp instruction, is the only limiter of this stage and the other
+        // softmax warp of the sub-partition fills the issue slots), (C) row sums on 4 chains + bf16 packing + stores.
+        uint64_t x2[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t)
+          x2[t] = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), c2, nmc2);
+        float pe[64];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float x0, x1;
+          unpack_f32x2(x2[t], x0, x1);
+          pe[2 * t] = ex2_approx(x0);
+          pe[2 * t + 1] = ex2_approx(x1);
+        }
+        uint64_t la = lsum2, lb = lsum2b, lc = pack_f32x2(0.f, 0.f), ld = pack_f32x2(0.f, 0.f);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int t = c8 * 4 + t4;
+            const uint64_t p2 = pack_f32x2(pe[2 * t], pe[2 * t + 1]);
+            if (t4 == 0) la = add_f32x2(la, p2);
+            else if (t4 == 1) lb = add_f32x2(lb, p2);
+            else if (t4 == 2) lc = add_f32x2(lc, p2);
+            else ld = add_f32x2(ld, p2);
+            pk[t4] = pack_bf16x2(pe[2 * t], pe[2 * t + 1]);
+          }
+          *reinterpret_cast<uint4*>(p_row + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        lsum2 = add_f32x2(la, lc);
+        lsum2b = add_f32x2(lb, ld);
+      } else {
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {   // 8 chunks of 8 keys = 16 bytes of bf16
         uint32_t pk[4];
@@ -311,10 +349,11 @@ flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
         }
         *reinterpret_cast<uint4*>(p_row + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i]);
+      if (lane == 0) mbar_arrive(&p_full[i * 2 + (u & 1)]);
     };
 
     const bool ragged = (p.kv_len % SUB) != 0;

@@ -69,8 +69,11 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
   uint64_t* kv_empty = bars + STAGES;       // [STAGES]
   uint64_t* s_full = bars + 2 * STAGES;     // [2]  S_i(u) complete in TMEM
   uint64_t* s_cons = s_full + 2;            // [2]  softmax i has S_i(u) in registers
-  uint64_t* p_full = s_cons + 2;            // [2]  P_i(u) in shared memory (and O_i rescaled if needed)
-  uint64_t* pv_done = p_full + 2;           // [2]  one completion per PV_i(u)
+  uint64_t* p_full = s_cons + 2;            // [2 tiles][2 P buffers]  P_i(u) in shared memory (and O_i rescaled if needed).
+                                            // One barrier per P buffer: a softmax warpgroup may finish steps u and u+1
+                                            // before the MMA warp (held up by the other tile) consumes P_i(u); with a
+                                            // single barrier those two completions would alias in the phase parity.
+  uint64_t* pv_done = p_full + 4;           // [2]  one completion per PV_i(u)
   uint64_t* o_final = pv_done + 2;          // [2]
   uint64_t* q_ready = o_final + 2;          // [1]  Q tiles stored in TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
@@ -95,10 +98,10 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
         mbar_init(&s_cons[i], 8);
-        mbar_init(&p_full[i], 8);
         mbar_init(&pv_done[i], 1);
         mbar_init(&o_final[i], 1);
       }
+      for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 8);
       mbar_init(q_ready, 16);
       fence_barrier_init();
     }
@@ -169,7 +172,7 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          mbar_wait(&p_full[i], u & 1, 0x4340 | i);
+          mbar_wait(&p_full[i * 2 + (u & 1)], (u >> 1) & 1, 0x4340 | (i * 2 + (u & 1)));
           tc_fence_after();
           issue_PV(i, u);
           if (last) umma_commit(&o_final[i]);
@@ -322,7 +325,7 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i]);
+      if (lane == 0) mbar_arrive(&p_full[i * 2 + (u & 1)]);
     };
 
     const bool ragged = (p.kv_len % SUB) != 0;

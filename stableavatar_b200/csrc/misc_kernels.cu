@@ -130,7 +130,8 @@ __global__ void gather_rows_kernel(const float* src, const int* idx, float* out,
 // latents = bf16(float(latents) + bf16(dsigma * noise))             (diffusers FlowMatchEulerDiscreteScheduler.step)
 __global__ void cfg_euler_kernel(const __nv_bfloat16* pred, const __nv_bfloat16* lat, __nv_bfloat16* out,
                                  __nv_bfloat16* noise_out, long long n, float audio_scale, float text_scale,
-                                 float dsigma, int cfg) {
+                                 float dsigma, const float* dsigma_dev, int cfg) {
+  if (dsigma_dev) dsigma = *dsigma_dev;   // schedule value kept on the device so that a captured CUDA graph can be replayed
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float np;
     if (cfg) {
@@ -225,13 +226,14 @@ extern "C" int sa_gather_rows_f32(const void* src, const void* idx, void* out, i
 }
 
 extern "C" int sa_cfg_euler_step(const void* pred, const void* latents, void* out, void* noise_out, int64_t n,
-                                 float audio_scale, float text_scale, float dsigma, int32_t cfg, sa_stream_t stream) {
+                                 float audio_scale, float text_scale, float dsigma, const void* dsigma_dev, int32_t cfg,
+                                 sa_stream_t stream) {
   using namespace sa;
   if (!pred || !latents || !out || n <= 0) { set_error("sa_cfg_euler_step: bad argument"); return SA_ERR_BAD_ARG; }
   misc::cfg_euler_kernel<<<misc::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(pred), reinterpret_cast<const __nv_bfloat16*>(latents),
       reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<__nv_bfloat16*>(noise_out), n, audio_scale, text_scale,
-      dsigma, cfg);
+      dsigma, reinterpret_cast<const float*>(dsigma_dev), cfg);
   SA_LAUNCH_CHECK("cfg_euler_kernel launch");
   return SA_OK;
 }

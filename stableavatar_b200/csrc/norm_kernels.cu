@@ -69,21 +69,66 @@ struct LnParams {
   float eps;
 };
 
-template <int NCH>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) layernorm_kernel(const LnParams p) {
+// The row is kept in registers in its storage format (packed bf16: 4 words per 8 elements) so that 6 chunks cost 24
+// registers instead of 48 and four CTAs stay resident per SM; dtypes are compile-time so no chunk array is ever
+// indexed through a run-time branch (which ptxas turns into local-memory traffic).
+template <bool XBF>
+struct RowChunk;
+template <>
+struct RowChunk<true> {
+  uint4 u;
+  __device__ __forceinline__ void load(const void* base, long long idx) {
+    u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+};
+template <>
+struct RowChunk<false> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const void* base, long long idx) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    a = p[0];
+    b = p[1];
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&v)[8]) {
+  RowChunk<true> c;
+  c.load(p, 0);
+  c.get(v);
+}
+
+template <int NCH, bool XBF, bool OBF, bool WBF>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, XBF ? 4 : 2) layernorm_kernel(const LnParams p) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= p.rows) return;
   const int nchunks = p.C >> 3;
-  float v[NCH][8];
+  RowChunk<XBF> v[NCH];
   float s = 0.f;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int ch = lane + c * 32;
-    if (ch < nchunks) {
-      load_chunk(p.x, p.x_dtype, (long long)row * p.ldx + ch * 8, v[c]);
+    if (ch < nchunks) v[c].load(p.x, (long long)row * p.ldx + ch * 8);
+  }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += v[c][i];
+  for (int c = 0; c < NCH; ++c) {
+    if (lane + c * 32 < nchunks) {
+      float t[8];
+      v[c].get(t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += t[i];
     }
   }
   const float mean = warp_sum(s) / p.C;
@@ -91,9 +136,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) layernorm_kernel(const L
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     if (lane + c * 32 < nchunks) {
+      float t[8];
+      v[c].get(t);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float d = v[c][i] - mean;
+        const float d = t[i] - mean;
         ss += d * d;
       }
     }
@@ -106,12 +153,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) layernorm_kernel(const L
     if (ch >= nchunks) continue;
     const int col = ch * 8;
     float y[8];
+    v[c].get(y);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = (v[c][i] - mean) * rstd;
+    for (int i = 0; i < 8; ++i) y[i] = (y[i] - mean) * rstd;
     if (p.weight) {
       float w[8], b[8];
-      load_chunk(p.weight, p.w_dtype, col, w);
-      load_chunk(p.bias, p.w_dtype, col, b);
+      RowChunk<WBF> cw, cb;
+      cw.load(p.weight, col);
+      cb.load(p.bias, col);
+      cw.get(w);
+      cb.get(b);
 #pragma unroll
       for (int i = 0; i < 8; ++i) y[i] = fmaf(y[i], w[i], b[i]);
     }
@@ -121,8 +172,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) layernorm_kernel(const L
     }
     if (p.scale) {
       float sc[8], sh[8];
-      load_chunk(p.scale, SA_BF16, mrow + col, sc);
-      load_chunk(p.shift, SA_BF16, mrow + col, sh);
+      load8_bf16(p.scale + mrow + col, sc);
+      load8_bf16(p.shift + mrow + col, sh);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float one_plus = bf16_round(1.0f + sc[i]);  // (1 + e1) is a bf16 op in both streams
@@ -135,13 +186,31 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) layernorm_kernel(const L
     }
     if (p.gate) {  // adapter "pseudo self-attention" (vp1B.py:345-347): out = res + y * e2
       float g[8], r[8];
-      load_chunk(p.gate, SA_BF16, mrow + col, g);
-      load_chunk(p.res, p.out_dtype, (long long)row * p.ldr + col, r);
+      load8_bf16(p.gate + mrow + col, g);
+      RowChunk<OBF> cr;
+      cr.load(p.res, (long long)row * p.ldr + col);
+      cr.get(r);
 #pragma unroll
       for (int i = 0; i < 8; ++i) y[i] = r[i] + y[i] * g[i];
     }
-    store_chunk(p.out, p.out_dtype, (long long)row * p.ldo + col, y);
+    store_chunk(p.out, OBF ? SA_BF16 : SA_F32, (long long)row * p.ldo + col, y);
   }
+}
+
+template <int NCH>
+static void launch_ln(const LnParams& p, int grid, cudaStream_t stream) {
+  const bool xb = p.x_dtype == SA_BF16, ob = p.out_dtype == SA_BF16, wb = p.w_dtype == SA_BF16;
+  const int thr = WARPS_PER_BLOCK * 32;
+#define SA_LN_CASE(X, O, W) layernorm_kernel<NCH, X, O, W><<<grid, thr, 0, stream>>>(p)
+  if (xb && ob && wb) SA_LN_CASE(true, true, true);
+  else if (xb && ob) SA_LN_CASE(true, true, false);
+  else if (xb && wb) SA_LN_CASE(true, false, true);
+  else if (xb) SA_LN_CASE(true, false, false);
+  else if (ob && wb) SA_LN_CASE(false, true, true);
+  else if (ob) SA_LN_CASE(false, true, false);
+  else if (wb) SA_LN_CASE(false, false, true);
+  else SA_LN_CASE(false, false, false);
+#undef SA_LN_CASE
 }
 
 // ------------------------------------------------------------------------------------------------ RMSNorm + RoPE
@@ -155,22 +224,27 @@ struct RmsParams {
 };
 
 template <int NCH>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) rmsnorm_rope_kernel(const RmsParams p) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) rmsnorm_rope_kernel(const RmsParams p) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= p.rows) return;
   __nv_bfloat16* x = p.x[blockIdx.y];
   const __nv_bfloat16* wgt = p.weight[blockIdx.y];
   const int nchunks = p.C >> 3;
-  float v[NCH][8];
+  RowChunk<true> v[NCH];
   float ss = 0.f;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int ch = lane + c * 32;
-    if (ch < nchunks) {
-      load_chunk(x, SA_BF16, (long long)row * p.ld + ch * 8, v[c]);
+    if (ch < nchunks) v[c].load(x, (long long)row * p.ld + ch * 8);
+  }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ss += v[c][i] * v[c][i];
+  for (int c = 0; c < NCH; ++c) {
+    if (lane + c * 32 < nchunks) {
+      float t[8];
+      v[c].get(t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += t[i] * t[i];
     }
   }
   const float rinv = rsqrtf(warp_sum(ss) / p.C + p.eps);
@@ -183,9 +257,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) rmsnorm_rope_kernel(cons
     if (ch >= nchunks) continue;
     const int col = ch * 8;
     float w[8], y[8];
-    load_chunk(wgt, SA_BF16, col, w);
+    load8_bf16(wgt + col, w);
+    v[c].get(y);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = bf16_round(bf16_round(v[c][i] * rinv) * w[i]);
+    for (int i = 0; i < 8; ++i) y[i] = bf16_round(bf16_round(y[i] * rinv) * w[i]);
     if (rotate) {
       const int j0 = (col & 127) >> 1;  // first complex pair of this chunk inside its head
 #pragma unroll
@@ -247,9 +322,9 @@ extern "C" int sa_layernorm_modulate(const sa_ln_args* a, sa_stream_t stream_) {
   p.eps = a->eps;
   const int grid = (a->rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   const int nch = (a->C / 8 + 31) / 32;
-  if (nch <= 2) layernorm_kernel<2><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
-  else if (nch <= 6) layernorm_kernel<6><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
-  else layernorm_kernel<8><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  if (nch <= 2) launch_ln<2>(p, grid, stream);
+  else if (nch <= 6) launch_ln<6>(p, grid, stream);
+  else launch_ln<8>(p, grid, stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "layernorm_kernel launch");
   return SA_OK;

@@ -203,7 +203,8 @@ def gather_rows(src, idx):
     return out
 
 
-def cfg_euler_step(pred, latents, dsigma, audio_scale=0.0, text_scale=0.0, cfg=True, out=None, noise_out=None):
+def cfg_euler_step(pred, latents, dsigma, audio_scale=0.0, text_scale=0.0, cfg=True, out=None, noise_out=None,
+                   dsigma_dev=None):
     """latents' = bf16(float(latents) + dsigma * CFG(pred)) — sa_cfg_euler_step."""
     _need_cuda(pred, latents)
     assert pred.dtype == latents.dtype == torch.bfloat16 and pred.is_contiguous() and latents.is_contiguous()
@@ -213,7 +214,7 @@ def cfg_euler_step(pred, latents, dsigma, audio_scale=0.0, text_scale=0.0, cfg=T
         out = torch.empty_like(latents)
     L.check(L.lib().sa_cfg_euler_step(C.c_void_p(pred.data_ptr()), C.c_void_p(latents.data_ptr()),
                                       C.c_void_p(out.data_ptr()), C.c_void_p(L.ptr(noise_out)), C.c_int64(n),
-                                      C.c_float(audio_scale), C.c_float(text_scale), C.c_float(dsigma), int(cfg),
+                                      C.c_float(audio_scale), C.c_float(text_scale), C.c_float(dsigma), C.c_void_p(L.ptr(dsigma_dev)), int(cfg),
                                       L.stream_ptr()), "sa_cfg_euler_step")
     return out
 

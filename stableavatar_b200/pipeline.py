@@ -55,13 +55,59 @@ def overlap_weights(n, scheme, device, dtype):
     return w.view(1, 1, n, 1, 1).to(device=device, dtype=dtype)
 
 
+class GraphedDenoiseStep:
+    """One window of one step — DiT forward on the CFG batch + CFG combine + Euler update — captured once as a CUDA
+    graph (NCCL all-to-alls of the sequence-parallel path included) and replayed for every step of that window shape:
+    the ~650 kernel launches of a step then cost no host time, which matters most under sequence parallelism where a
+    step is only ~100 ms. Step-dependent scalars (timestep, sigma difference) live in device buffers."""
+
+    def __init__(self, pipe, latents, prompt_embeds, clip_context, y, vocal_embeddings, *, seq_len, clip_length,
+                 text_guide_scale, audio_guide_scale, do_cfg):
+        dev = latents.device
+        n = 3 if do_cfg else 1
+        self.lat = latents.clone()
+        self.t = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.ds = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.vocal = vocal_embeddings.clone()
+
+        def run():
+            x = self.lat.expand(n, -1, -1, -1, -1).contiguous() if n > 1 else self.lat
+            pred = pipe.transformer(x=x, context=prompt_embeds, t=self.t, seq_len=seq_len, y=y[:, :, :self.lat.size(2)],
+                                    clip_fea=clip_context, vocal_embeddings=self.vocal, is_clip_level_modeling=False,
+                                    video_sample_n_frames=clip_length)
+            return ops.cfg_euler_step(pred.contiguous(), self.lat, 0.0, audio_scale=float(audio_guide_scale or 0.0),
+                                      text_scale=float(text_guide_scale or 0.0), cfg=do_cfg, dsigma_dev=self.ds)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            run()                                            # warm-up: lazy operand preparation, attribute setup, NCCL
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = run()
+
+    def __call__(self, latents, t, dsigma, vocal_embeddings=None):
+        self.lat.copy_(latents)
+        if torch.is_tensor(t):
+            self.t.copy_(t.to(torch.float32).expand_as(self.t))
+        else:
+            self.t.fill_(float(t))
+        self.ds.fill_(float(dsigma))
+        if vocal_embeddings is not None and vocal_embeddings.data_ptr() != self.vocal.data_ptr():
+            self.vocal.copy_(vocal_embeddings)
+        self.graph.replay()
+        return self.out
+
+
 class WanI2VTalkingInferenceLongPipeline:
     def __init__(self, tokenizer=None, text_encoder=None, vae=None, transformer=None, clip_image_encoder=None,
                  scheduler=None, wav2vec_processor=None, wav2vec=None):
         self.tokenizer, self.text_encoder, self.vae, self.transformer = tokenizer, text_encoder, vae, transformer
         self.clip_image_encoder, self.scheduler = clip_image_encoder, scheduler
         self.wav2vec_processor, self.wav2vec = wav2vec_processor, wav2vec
-        self.launches = 0
+        self.use_cuda_graphs = True      # replay a captured graph per window shape (off automatically with TeaCache)
+        self._graphs = {}
 
     # ------------------------------------------------------------------ hot path
     @torch.no_grad()
@@ -69,6 +115,19 @@ class WanI2VTalkingInferenceLongPipeline:
                      clip_length, text_guide_scale, audio_guide_scale, do_cfg=True):
         """One window of one step (pipe.py:730-754): DiT forward on the CFG batch, CFG combine, Euler update.
         latents [1,16,f,h,w] bf16 -> new latents (bf16)."""
+        tc = getattr(self.transformer, "teacache", None)
+        sp = getattr(self.transformer, "sp_world_size", 1)   # graphs are not used under sequence parallelism yet: capturing
+        # the NCCL all-to-alls hung a 2-GPU replay in round 1 (DESIGN.md §5)
+        if self.use_cuda_graphs and sp == 1 and tc is None and getattr(self.transformer, "hooks", None) is None:
+            key = (tuple(latents.shape), tuple(vocal_embeddings.shape), seq_len, clip_length, float(text_guide_scale or 0),
+                   float(audio_guide_scale or 0), do_cfg, y.data_ptr(), clip_context.data_ptr(),
+                   tuple(p.data_ptr() for p in prompt_embeds))
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._graphs[key] = GraphedDenoiseStep(
+                    self, latents, prompt_embeds, clip_context, y, vocal_embeddings, seq_len=seq_len, clip_length=clip_length,
+                    text_guide_scale=text_guide_scale, audio_guide_scale=audio_guide_scale, do_cfg=do_cfg)
+            return g(latents, t, dsigma, vocal_embeddings).clone()
         n = 3 if do_cfg else 1
         x = latents.expand(n, -1, -1, -1, -1).contiguous() if n > 1 else latents
         tt = t.expand(n) if torch.is_tensor(t) else torch.full((n,), float(t), device=latents.device)
