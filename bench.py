@@ -26,6 +26,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "s/denoise-step 1.3B @480x832x81f"
+SELF_ATTN_DRAM_BYTES_B3 = 913.43e6 + 285.35e6   # measured once with ncu on this command, see profiles/
 UNIT = "s/step"
 
 
@@ -267,6 +268,24 @@ def run_b200(args):
     s_per_step = ms.item() / 1e3 / args.steps
     s_e2e = ms_e2e.item() / 1e3 / args.steps
 
+    vae_s = None
+    if rank == 0 and not args.no_vae:
+        # BASELINE "e2e s/clip": the clip = 50 denoise steps + one Wan VAE decode of the final latents (pipe.py:793-799)
+        from stableavatar_b200.wan_vae import AutoencoderKLWan
+        vae = AutoencoderKLWan()
+        vae.load_state_dict(synth.vae_state_dict(), strict=True)
+        vae = vae.to(dev)
+        z = synth.det_normal("bench_z", (1, 16, F_lat, h, w)).to(dev)
+        vae.decode(z[:, :, :2])                              # warm-up: operand preparation
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        video = vae.decode(z).sample
+        ev1.record()
+        torch.cuda.synchronize()
+        vae_s = ev0.elapsed_time(ev1) / 1e3
+        assert video.shape == (1, 3, args.frames, args.height, args.width)
+        del vae, video
     if rank == 0:
         peaks = load_peaks()
         total_flops, attn_flops_per_launch = step_flops(cfg, L)
@@ -287,10 +306,16 @@ def run_b200(args):
                        "bf16_peak_frac_step": total_flops / s_per_step / 1e12 / world / peaks["bf16"],
                        "launch_mode": "eager" if (args.no_graph or world > 1) else "cuda-graph replay (value, e2e); kernel timing and "
                                       "gpu_launches from an eager pass of the same steps",
-                       "eager_ms_per_step": ms_eager / args.steps, "kernel_time_share": shares},
+                       "eager_ms_per_step": ms_eager / args.steps, "kernel_time_share": shares,
+                       "vae_decode_s": vae_s, "clip_s": None if vae_s is None else 50 * s_per_step + vae_s,
+                       "clip_s_note": "50 denoise steps x value + one VAE decode (21x60x104 latent -> 81x480x832), "
+                                      "decode on one GPU (replicas only)"},
             "roofline": {"kernel": "flash_attn_d128_kernel (self-attention)", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"] if achieved else None,
-                         "traffic": None, "peak_source": f"{peaks['src']} sustained bf16 (MEASURED_PEAKS.json)",
+                         "traffic": SELF_ATTN_DRAM_BYTES_B3 / world if (args.frames, args.height, args.width) == (81, 480, 832) else None,
+                         "traffic_source": "profiles/r01_selfattn_in_bench_ncu.txt (ncu --set full, dram__bytes_read+write of one "
+                                           "B=3 self-attention launch; algorithmic q+k+v+o = 1208 MB)",
+                         "peak_source": f"{peaks['src']} sustained bf16 (MEASURED_PEAKS.json)",
                          "launches_timed": len(attn_ms), "avg_launch_ms": attn_avg},
             "e2e": {"value": s_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_host.numel() * 2},
             "gpu_launches": launches, "clocks": clocks,
@@ -317,6 +342,7 @@ def main():
     ap.add_argument("--width", type=int, default=832)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="e2e region without CUDA-graph replay")
+    ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode timing that feeds config.clip_s")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
