@@ -359,7 +359,6 @@ flash_attn_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 }  // namespace sa
 
 int sa_flash_attn_d128_v4(const sa_attn_args* a, int poly, cudaStream_t stream);  // attn_v4_tcgen05.cu
-int sa_flash_attn_d128_v5(const sa_attn_args* a, int poly, cudaStream_t stream);  // attn_v5_tcgen05.cu
 
 extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
   using namespace sa;
@@ -384,7 +383,6 @@ extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
     if (poly_env < 0 || poly_env > 4) poly_env = kDefaultPolyPairs;
   }
   if (impl == 4) return sa_flash_attn_d128_v4(a, poly_env, stream);
-  if (impl == 5) return sa_flash_attn_d128_v5(a, poly_env, stream);
   CUtensorMap tq, tk, tv;
   auto mk = [&](CUtensorMap* m, const void* base, int len, long long ls, long long bs) {
     uint64_t dims[4] = {(uint64_t)D, (uint64_t)len, (uint64_t)a->heads, (uint64_t)a->batch};

@@ -58,6 +58,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// Non-blocking probe (try_wait may suspend the thread for a hardware-defined interval; test_wait never does).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait. `tag` identifies the barrier (kernel id in the high byte) in the diagnostic line.
 static __device__ __noinline__ void mbar_fault(uint32_t tag) {
   printf("[sa_b200] mbarrier wait timed out: tag=0x%x block=(%d,%d,%d) thread=%d\n", tag, blockIdx.x, blockIdx.y,
