@@ -31,65 +31,63 @@ def plan(num_heads: int, world: int, rank: int) -> SimpleNamespace:
                            q_sources=[r for r in range(world) if r % qs == rank % qs])
 
 
-def all_to_all(outputs, inputs, group=None):
-    """List all-to-all (ragged allowed). NCCL: one grouped collective over NVLink. gloo (CPU tests): isend/irecv."""
+def all_to_all_single(out, inp, out_splits, in_splits, group=None):
+    """Ragged all-to-all on flat buffers (split sizes in elements, rank order). NCCL: one grouped collective over
+    NVLink. gloo (CPU tests) has no all_to_all: isend/irecv on the slices."""
     if dist.get_backend(group) == "nccl":
-        dist.all_to_all(outputs, inputs, group=group)
+        dist.all_to_all_single(out, inp, out_splits, in_splits, group=group)
         return
-    rank = dist.get_rank(group)
-    outputs[rank].copy_(inputs[rank])
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    io = [sum(in_splits[:r]) for r in range(world + 1)]
+    oo = [sum(out_splits[:r]) for r in range(world + 1)]
+    out[oo[rank]:oo[rank + 1]].copy_(inp[io[rank]:io[rank + 1]])
     reqs = []
-    for r in range(dist.get_world_size(group)):
+    for r in range(world):
         if r == rank:
             continue
         peer = dist.get_global_rank(group, r) if group is not None else r
-        if inputs[r].numel():
-            reqs.append(dist.isend(inputs[r].contiguous(), peer, group=group))
-        if outputs[r].numel():
-            reqs.append(dist.irecv(outputs[r], peer, group=group))
+        if in_splits[r]:
+            reqs.append(dist.isend(inp[io[r]:io[r + 1]].contiguous(), peer, group=group))
+        if out_splits[r]:
+            reqs.append(dist.irecv(out[oo[r]:oo[r + 1]], peer, group=group))
     for q in reqs:
         q.wait()
 
 
-def exchange_qkv(pl, q, k, v, group=None):
-    """q, k, v: local [B, Ll, nh, d] views. Returns (Q [Lq, B, hp, d], KV [L, B, 2, hp, d]) for this rank's head group:
-    all tokens for K/V, the tokens of `pl.q_sources` (in rank order) for Q. Token-major so that the token stride is
-    uniform for the attention kernel's TMA descriptors."""
+def exchange_qkv(pl, q, k, v, group=None, kv=None):
+    """q, k, v: local [B, Ll, nh, d] views of one fused projection buffer. Returns (Q [Lq, B, hp, d],
+    KV [L, B, 2, hp, d]) for this rank's head group: all tokens for K/V, the tokens of `pl.q_sources` (in rank order)
+    for Q. Token-major so that the gathered sequence has a uniform token stride for the attention kernel's TMA
+    descriptors; the receive buffers are used as they land (no unpack), the send side is two permuted copies."""
     B, Ll, nh, d = q.shape
-    P, hp = pl.world, pl.hp
-    send, recv = [], []
-    for dst in range(P):
-        g, s = dst // pl.qs, dst % pl.qs
-        hs = slice(g * hp, (g + 1) * hp)
-        kv = torch.stack([k[:, :, hs], v[:, :, hs]], dim=2).permute(1, 0, 2, 3, 4)          # [Ll, B, 2, hp, d]
-        parts = [kv.reshape(-1)]
-        if pl.rank % pl.qs == s:
-            parts.append(q[:, :, hs].permute(1, 0, 2, 3).reshape(-1))
-        send.append(torch.cat(parts))
+    P, hp, hg, qs = pl.world, pl.hp, pl.hg, pl.qs
     n_kv, n_q = Ll * B * 2 * hp * d, Ll * B * hp * d
-    for src in range(P):
-        recv.append(torch.empty(n_kv + (n_q if src in pl.q_sources else 0), device=q.device, dtype=q.dtype))
-    all_to_all(recv, send, group)
-    KV = torch.stack([r[:n_kv].view(Ll, B, 2, hp, d) for r in recv]).view(P * Ll, B, 2, hp, d)
-    Q = torch.stack([recv[src][n_kv:].view(Ll, B, hp, d) for src in pl.q_sources]).view(len(pl.q_sources) * Ll, B, hp, d)
-    return Q, KV
+    # K|V for head group g -> every rank of that group: [hg, Ll, B, 2, hp, d], repeated for the qs query splits
+    if kv is None:                                           # kv: optional [B, Ll, 2, nh, d] view holding k and v side by side
+        kv = torch.stack([k, v], dim=2)
+    kv = kv.reshape(B, Ll, 2, hg, hp, d).permute(3, 1, 0, 2, 4, 5)
+    kv_send = (kv.repeat_interleave(qs, dim=0) if qs > 1 else kv.contiguous()).reshape(-1)
+    kv_recv = torch.empty(P * n_kv, device=q.device, dtype=q.dtype)
+    all_to_all_single(kv_recv, kv_send, [n_kv] * P, [n_kv] * P, group)
+    # Q for head group g -> only the rank (g, s = my query split): [hg, Ll, B, hp, d]
+    q_send = q.view(B, Ll, hg, hp, d).permute(2, 1, 0, 3, 4).contiguous().reshape(-1)
+    in_splits = [n_q if dst % qs == pl.s else 0 for dst in range(P)]
+    out_splits = [n_q if src in pl.q_sources else 0 for src in range(P)]
+    q_recv = torch.empty(len(pl.q_sources) * n_q, device=q.device, dtype=q.dtype)
+    all_to_all_single(q_recv, q_send, out_splits, in_splits, group)
+    return q_recv.view(len(pl.q_sources) * Ll, B, hp, d), kv_recv.view(P * Ll, B, 2, hp, d)
 
 
 def exchange_out(pl, O, B, Ll, nh, d, group=None):
     """O: [Lq, B, hp, d] attention output of this rank (its head group, the tokens of pl.q_sources). Returns the local
     [B, Ll, nh, d] with every head group filled in by its owner."""
-    P, hp = pl.world, pl.hp
+    P, hp, hg, qs = pl.world, pl.hp, pl.hg, pl.qs
     n = Ll * B * hp * d
-    Os = O.view(len(pl.q_sources), Ll, B, hp, d)
-    send = [Os[pl.q_sources.index(dst)].reshape(-1) if dst in pl.q_sources else O.new_empty(0) for dst in range(P)]
-    recv = [O.new_empty(n if src % pl.qs == pl.rank % pl.qs else 0) for src in range(P)]
-    all_to_all(recv, send, group)
-    out = O.new_empty(B, Ll, nh, d)
-    for src in range(P):
-        if recv[src].numel():
-            g = src // pl.qs
-            out[:, :, g * hp:(g + 1) * hp] = recv[src].view(Ll, B, hp, d).permute(1, 0, 2, 3)
-    return out
+    in_splits = [n if dst in pl.q_sources else 0 for dst in range(P)]       # O is already ordered by source rank
+    out_splits = [n if src % qs == pl.s else 0 for src in range(P)]         # one block per head-group owner
+    recv = torch.empty(hg * n, device=O.device, dtype=O.dtype)
+    all_to_all_single(recv, O.reshape(-1), out_splits, in_splits, group)
+    return recv.view(hg, Ll, B, hp, d).permute(2, 1, 0, 3, 4).reshape(B, Ll, nh, d)
 
 
 # ---------------------------------------------------------------------------------------------- model hooks
@@ -110,7 +108,7 @@ def self_attention(model, qkv, sa, st):
     ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
                       grid=st["grid"], rows_per_batch=Ll, tok_offset=st["tok0"])
     q5 = qkv.view(B, Ll, 3, nh, 128)
-    Q, KV = exchange_qkv(pl, q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], model.sp_group)
+    Q, KV = exchange_qkv(pl, q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], model.sp_group, kv=q5[:, :, 1:3])
     with ops.timed("self_attn"):
         O = ops.flash_attn(Q.transpose(0, 1), KV[:, :, 0].transpose(0, 1), KV[:, :, 1].transpose(0, 1),
                            out=torch.empty_like(Q).transpose(0, 1))
