@@ -35,7 +35,8 @@ constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = (2 + 2 * KV_STAGES) * TILE_BYTES + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kDefaultPolyPairs = 0;       // of every 8 column pairs, how many use the FMA-pipe exp2 (SA_ATTN_POLY overrides)
-constexpr int kDefaultImpl = 4;            // 2: this file; 4: decoupled kernel of attn_v4_tcgen05.cu (SA_ATTN_IMPL overrides)
+constexpr int kDefaultImpl = 8;            // 2: this file; 4: decoupled kernel (attn_v4_tcgen05.cu); 8: decoupled + one
+                                           // MMA-issuing warp per Q tile (attn_v8_tcgen05.cu). SA_ATTN_IMPL overrides.
 
 struct Params {
   __nv_bfloat16* out;
@@ -359,6 +360,7 @@ flash_attn_d128_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 }  // namespace sa
 
 int sa_flash_attn_d128_v4(const sa_attn_args* a, int poly, cudaStream_t stream);  // attn_v4_tcgen05.cu
+int sa_flash_attn_d128_v8(const sa_attn_args* a, int poly, cudaStream_t stream);  // attn_v8_tcgen05.cu
 
 extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
   using namespace sa;
@@ -383,6 +385,7 @@ extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
     if (poly_env < 0 || poly_env > 4) poly_env = kDefaultPolyPairs;
   }
   if (impl == 4) return sa_flash_attn_d128_v4(a, poly_env, stream);
+  if (impl == 8) return sa_flash_attn_d128_v8(a, poly_env, stream);
   CUtensorMap tq, tk, tv;
   auto mk = [&](CUtensorMap* m, const void* base, int len, long long ls, long long bs) {
     uint64_t dims[4] = {(uint64_t)D, (uint64_t)len, (uint64_t)a->heads, (uint64_t)a->batch};
