@@ -8,6 +8,6 @@ timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpuru
 tail -1 gpurun_out/bench.log | cut -c1-2500; tail -3 gpurun_out/bench.err
 SHORT="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph --no-vae"
 timeout 300 $SHORT > gpurun_out/plain.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:flash_attn_v4 -s 8 -c 1 -o gpurun_out/prof_selfattn_bench $SHORT > gpurun_out/ncu_attn_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:flash_attn_v -s 8 -c 1 -o gpurun_out/prof_selfattn_bench $SHORT > gpurun_out/ncu_attn_bench.log 2>&1
 echo "ncu attn exit $?"
 ls -la gpurun_out | head -30
