@@ -188,6 +188,64 @@ class WanTransformer3DFantasyModel(nn.Module):
         self.vocal_projector._prep = None
         return super().load_state_dict(state_dict, strict=strict, assign=assign)
 
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        import inspect
+        keys = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        merged = {**config, **kwargs}
+        return cls(**{k: v for k, v in merged.items() if k in keys})
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, subfolder=None, transformer_additional_kwargs={},
+                        low_cpu_mem_usage=False, torch_dtype=torch.bfloat16):
+        """Same contract as 1B.py:1210-1338: `config.json` + `diffusion_pytorch_model.{bin,safetensors}` (or every
+        `*.safetensors` in the directory); `dict_mapping` renames config keys; a checkpoint whose patch embedding has
+        fewer input channels is zero-padded (:1316-1320); tensors whose shape does not match are skipped (:1322-1329);
+        non-strict load; result cast to `torch_dtype`. `low_cpu_mem_usage` only changes how the reference
+        materialises the weights and is accepted for compatibility."""
+        import glob
+        import json
+        import os
+        if subfolder is not None:
+            pretrained_model_path = os.path.join(pretrained_model_path, subfolder)
+        print(f"loaded 3D transformer's pretrained weights from {pretrained_model_path} ...")
+        config_file = os.path.join(pretrained_model_path, "config.json")
+        if not os.path.isfile(config_file):
+            raise RuntimeError(f"{config_file} does not exist")
+        with open(config_file, "r") as f:
+            config = json.load(f)
+        kw = dict(transformer_additional_kwargs)
+        for key, dst in kw.pop("dict_mapping", {}).items():
+            kw[dst] = config[key]
+        kw.update(patch_size=(1, 2, 2), qk_norm=True, window_size=(-1, -1), cross_attn_norm=True)
+        model = cls.from_config(config, **kw)
+        model_file = os.path.join(pretrained_model_path, "diffusion_pytorch_model.bin")
+        model_file_safetensors = model_file.replace(".bin", ".safetensors")
+        if os.path.exists(model_file):
+            state_dict = torch.load(model_file, map_location="cpu")
+        else:
+            from safetensors.torch import load_file
+            files = [model_file_safetensors] if os.path.exists(model_file_safetensors) else \
+                sorted(glob.glob(os.path.join(pretrained_model_path, "*.safetensors")))
+            state_dict = {}
+            for f in files:
+                state_dict.update(load_file(f))
+        own = model.state_dict()
+        if "patch_embedding.weight" in state_dict and own["patch_embedding.weight"].size() != state_dict["patch_embedding.weight"].size():
+            w = torch.zeros_like(own["patch_embedding.weight"], dtype=state_dict["patch_embedding.weight"].dtype)
+            cin = state_dict["patch_embedding.weight"].size(1)
+            w[:, :cin] = state_dict["patch_embedding.weight"]
+            state_dict["patch_embedding.weight"] = w
+        kept = {}
+        for key, val in state_dict.items():
+            if key in own and own[key].size() == val.size():
+                kept[key] = val
+            else:
+                print(key, "Size don't match, skip")
+        m, u = model.load_state_dict(kept, strict=False)
+        print(f"### missing keys: {len(m)}; \n### unexpected keys: {len(u)};")
+        return model.to(torch_dtype)
+
     def _apply(self, fn, *a, **k):
         self._prep = None
         self.vocal_projector._prep = None

@@ -116,6 +116,21 @@ class AutoencoderKLWan(nn.Module):
         self._prep = None
         return super()._apply(fn, *a, **k)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, additional_kwargs={}):
+        """wan_vae.py:683-704: raw `.pth` / `.safetensors` state dict whose keys get the `model.` prefix."""
+        import inspect
+        keys = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        model = cls(**{k: v for k, v in additional_kwargs.items() if k in keys})
+        if pretrained_model_path.endswith(".safetensors"):
+            from safetensors.torch import load_file
+            state_dict = load_file(pretrained_model_path)
+        else:
+            state_dict = torch.load(pretrained_model_path, map_location="cpu")
+        m, u = model.load_state_dict({"model." + k: v for k, v in state_dict.items()}, strict=False)
+        print(f"### missing keys: {len(m)}; \n### unexpected keys: {len(u)};")
+        return model
+
     def encode(self, x, return_dict=True):
         raise NotImplementedError("AutoencoderKLWan (B200): encode is outside the accelerated hot path (SURVEY.md §8f); "
                                   "use the reference VAE for the one conditioning encode or pass latents directly")

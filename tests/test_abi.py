@@ -67,3 +67,35 @@ def test_model_state_dict_keys_match_reference_names():
 
 
 import torch  # noqa: E402
+
+
+def test_from_pretrained_roundtrip(tmp_path):
+    """Checkpoint directory contract of 1B.py:1210-1338 (config.json + safetensors, dict_mapping, in-channel padding)."""
+    import json
+    from safetensors.torch import save_file
+    from stableavatar_b200 import synth
+    from stableavatar_b200.wan_transformer3d import WanTransformer3DFantasyModel
+    cfg = dict(synth.DIT_TINY, num_layers=1, in_dim=16)
+    sd = synth.dit_state_dict(cfg)
+    (tmp_path / "transformer").mkdir()
+    json.dump({"in_dim": 36, "dim": 1536, "ffn_dim": cfg["ffn_dim"], "num_heads": 12, "num_layers": 1, "model_type": "i2v",
+               "text_dim": cfg["text_dim"], "text_len": cfg["text_len"], "freq_dim": 256, "out_dim": 16, "eps": 1e-6,
+               "unknown_key": 1}, open(tmp_path / "transformer" / "config.json", "w"))
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "transformer" / "diffusion_pytorch_model.safetensors"))
+    m = WanTransformer3DFantasyModel.from_pretrained(str(tmp_path), subfolder="transformer",
+                                                     transformer_additional_kwargs={"dict_mapping": {"in_dim": "in_channels"}},
+                                                     torch_dtype=torch.bfloat16)
+    assert m.dtype == torch.bfloat16 and m.in_dim == 36 and m.num_layers == 1
+    w = m.patch_embedding.weight
+    assert torch.equal(w[:, :16].float(), sd["patch_embedding.weight"].bfloat16().float()) and w[:, 16:].abs().max() == 0
+    assert torch.equal(m.blocks[0].ffn[0].weight.float(), sd["blocks.0.ffn.0.weight"].bfloat16().float())
+
+
+def test_vae_from_pretrained(tmp_path):
+    from stableavatar_b200 import synth
+    from stableavatar_b200.wan_vae import AutoencoderKLWan
+    sd = synth.vae_state_dict()
+    torch.save({k[len("model."):]: v for k, v in sd.items()}, tmp_path / "vae.pth")
+    m = AutoencoderKLWan.from_pretrained(str(tmp_path / "vae.pth"), additional_kwargs={"spatial_compression_ratio": 8})
+    assert torch.equal(m.state_dict()["model.decoder.conv1.weight"], sd["model.decoder.conv1.weight"])
+    assert (m.config.latent_channels, m.config.temporal_compression_ratio, m.config.spacial_compression_ratio) == (16, 4, 8)
