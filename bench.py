@@ -304,7 +304,7 @@ def run_b200(args):
                        "step_tflop": total_flops / 1e12,
                        "step_tflops_achieved": total_flops / s_per_step / 1e12 / world,
                        "bf16_peak_frac_step": total_flops / s_per_step / 1e12 / world / peaks["bf16"],
-                       "launch_mode": "eager" if (args.no_graph or world > 1) else "cuda-graph replay (value, e2e); kernel timing and "
+                       "launch_mode": "eager" if args.no_graph else "cuda-graph replay (value, e2e; NCCL calls eager between graph segments); kernel timing and "
                                       "gpu_launches from an eager pass of the same steps",
                        "eager_ms_per_step": ms_eager / args.steps, "kernel_time_share": shares,
                        "vae_decode_s": vae_s, "clip_s": None if vae_s is None else 50 * s_per_step + vae_s,

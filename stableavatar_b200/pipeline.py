@@ -56,10 +56,11 @@ def overlap_weights(n, scheme, device, dtype):
 
 
 class GraphedDenoiseStep:
-    """One window of one step — DiT forward on the CFG batch + CFG combine + Euler update — captured once as a CUDA
-    graph (NCCL all-to-alls of the sequence-parallel path included) and replayed for every step of that window shape:
-    the ~650 kernel launches of a step then cost no host time, which matters most under sequence parallelism where a
-    step is only ~100 ms. Step-dependent scalars (timestep, sigma difference) live in device buffers."""
+    """One window of one step — DiT forward on the CFG batch + CFG combine + Euler update — captured once as CUDA
+    graph(s) and replayed for every step of that window shape: the ~650 kernel launches of a step (≈ 80 ms of host
+    time) then cost nothing, which matters most under sequence parallelism where a step is only ~100 ms of GPU work.
+    Under sequence parallelism the NCCL all-to-alls stay eager and split the capture into segments
+    (sequence_parallel.SegmentedGraph). Step-dependent scalars (timestep, sigma difference) live in device buffers."""
 
     def __init__(self, pipe, latents, prompt_embeds, clip_context, y, vocal_embeddings, *, seq_len, clip_length,
                  text_guide_scale, audio_guide_scale, do_cfg):
@@ -78,14 +79,8 @@ class GraphedDenoiseStep:
             return ops.cfg_euler_step(pred.contiguous(), self.lat, 0.0, audio_scale=float(audio_guide_scale or 0.0),
                                       text_scale=float(text_guide_scale or 0.0), cfg=do_cfg, dsigma_dev=self.ds)
 
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            run()                                            # warm-up: lazy operand preparation, attribute setup, NCCL
-        torch.cuda.current_stream(dev).wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = run()
+        from .sequence_parallel import SegmentedGraph
+        self.graph = SegmentedGraph(run, device=dev)
 
     def __call__(self, latents, t, dsigma, vocal_embeddings=None):
         self.lat.copy_(latents)
@@ -96,8 +91,7 @@ class GraphedDenoiseStep:
         self.ds.fill_(float(dsigma))
         if vocal_embeddings is not None and vocal_embeddings.data_ptr() != self.vocal.data_ptr():
             self.vocal.copy_(vocal_embeddings)
-        self.graph.replay()
-        return self.out
+        return self.graph.replay()
 
 
 class WanI2VTalkingInferenceLongPipeline:
@@ -116,9 +110,7 @@ class WanI2VTalkingInferenceLongPipeline:
         """One window of one step (pipe.py:730-754): DiT forward on the CFG batch, CFG combine, Euler update.
         latents [1,16,f,h,w] bf16 -> new latents (bf16)."""
         tc = getattr(self.transformer, "teacache", None)
-        sp = getattr(self.transformer, "sp_world_size", 1)   # graphs are not used under sequence parallelism yet: capturing
-        # the NCCL all-to-alls hung a 2-GPU replay in round 1 (DESIGN.md §5)
-        if self.use_cuda_graphs and sp == 1 and tc is None and getattr(self.transformer, "hooks", None) is None:
+        if self.use_cuda_graphs and tc is None and getattr(self.transformer, "hooks", None) is None:
             key = (tuple(latents.shape), tuple(vocal_embeddings.shape), seq_len, clip_length, float(text_guide_scale or 0),
                    float(audio_guide_scale or 0), do_cfg, y.data_ptr(), clip_context.data_ptr(),
                    tuple(p.data_ptr() for p in prompt_embeds))

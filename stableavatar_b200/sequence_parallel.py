@@ -31,6 +31,68 @@ def plan(num_heads: int, world: int, rank: int) -> SimpleNamespace:
                            q_sources=[r for r in range(world) if r % qs == rank % qs])
 
 
+class SegmentedGraph:
+    """A function captured as a chain of CUDA graphs separated by eagerly issued communication calls.
+
+    Capturing the NCCL all-to-alls themselves inside one graph hung a 2-GPU replay (round 1), so only the compute
+    between them is captured: whenever the traced function reaches `comm_point(closure)` the current capture is closed,
+    the closure (a NCCL call on static buffers) runs eagerly and is recorded, and a new capture begins. All segments
+    share one memory pool, so tensors produced in one segment stay valid for the next ones and for every replay.
+    With no communication (single GPU) this degenerates to one ordinary CUDA graph."""
+    _active = None
+
+    def __init__(self, fn, device=None):
+        self.segments, self.cur = [], None
+        self.pool = torch.cuda.graph_pool_handle()
+        self.stream = torch.cuda.Stream(device=device)
+        self.stream.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(self.stream):
+            fn()                                         # warm-up: lazy operand preparation, attribute setup, NCCL init
+        torch.cuda.current_stream(device).wait_stream(self.stream)
+        torch.cuda.synchronize(device)
+        SegmentedGraph._active = self
+        try:
+            with torch.cuda.stream(self.stream):
+                self._begin()
+                self.out = fn()
+                self._end()
+        finally:
+            SegmentedGraph._active = None
+        torch.cuda.current_stream(device).wait_stream(self.stream)
+
+    def _begin(self):
+        self.cur = torch.cuda.CUDAGraph()
+        self.cur.capture_begin(pool=self.pool)
+
+    def _end(self):
+        self.cur.capture_end()
+        self.segments.append(self.cur)
+        self.cur = None
+
+    def comm(self, closure):
+        self._end()
+        closure()
+        self.segments.append(closure)
+        self._begin()
+
+    def replay(self):
+        for seg in self.segments:
+            if isinstance(seg, torch.cuda.CUDAGraph):
+                seg.replay()
+            else:
+                seg()
+        return self.out
+
+
+def comm_point(closure):
+    """Run a communication closure now; under SegmentedGraph capture it also splits the graph there."""
+    sg = SegmentedGraph._active
+    if sg is None:
+        closure()
+    else:
+        sg.comm(closure)
+
+
 def all_to_all_single(out, inp, out_splits, in_splits, group=None):
     """Ragged all-to-all on flat buffers (split sizes in elements, rank order). NCCL: one grouped collective over
     NVLink. gloo (CPU tests) has no all_to_all: isend/irecv on the slices."""
@@ -68,13 +130,16 @@ def exchange_qkv(pl, q, k, v, group=None, kv=None):
     kv = kv.reshape(B, Ll, 2, hg, hp, d).permute(3, 1, 0, 2, 4, 5)
     kv_send = (kv.repeat_interleave(qs, dim=0) if qs > 1 else kv.contiguous()).reshape(-1)
     kv_recv = torch.empty(P * n_kv, device=q.device, dtype=q.dtype)
-    all_to_all_single(kv_recv, kv_send, [n_kv] * P, [n_kv] * P, group)
     # Q for head group g -> only the rank (g, s = my query split): [hg, Ll, B, hp, d]
     q_send = q.view(B, Ll, hg, hp, d).permute(2, 1, 0, 3, 4).contiguous().reshape(-1)
     in_splits = [n_q if dst % qs == pl.s else 0 for dst in range(P)]
     out_splits = [n_q if src in pl.q_sources else 0 for src in range(P)]
     q_recv = torch.empty(len(pl.q_sources) * n_q, device=q.device, dtype=q.dtype)
-    all_to_all_single(q_recv, q_send, out_splits, in_splits, group)
+
+    def exchange():
+        all_to_all_single(kv_recv, kv_send, [n_kv] * P, [n_kv] * P, group)
+        all_to_all_single(q_recv, q_send, out_splits, in_splits, group)
+    comm_point(exchange)
     return q_recv.view(len(pl.q_sources) * Ll, B, hp, d), kv_recv.view(P * Ll, B, 2, hp, d)
 
 
@@ -86,7 +151,8 @@ def exchange_out(pl, O, B, Ll, nh, d, group=None):
     in_splits = [n if dst in pl.q_sources else 0 for dst in range(P)]       # O is already ordered by source rank
     out_splits = [n if src % qs == pl.s else 0 for src in range(P)]         # one block per head-group owner
     recv = torch.empty(hg * n, device=O.device, dtype=O.dtype)
-    all_to_all_single(recv, O.reshape(-1), out_splits, in_splits, group)
+    send = O.reshape(-1)
+    comm_point(lambda: all_to_all_single(recv, send, out_splits, in_splits, group))
     return recv.view(hg, Ll, B, hp, d).permute(2, 1, 0, 3, 4).reshape(B, Ll, nh, d)
 
 
@@ -133,5 +199,6 @@ def gather_tokens(model, u):
     """Gather the 64-wide head output of every shard (instead of the 1536-wide hidden states, 1B.py:1150-1154)."""
     P = model.sp_world_size
     parts = [torch.empty_like(u) for _ in range(P)]
-    dist.all_gather(parts, u.contiguous(), group=model.sp_group)
+    src = u.contiguous()
+    comm_point(lambda: dist.all_gather(parts, src, group=model.sp_group))
     return torch.cat(parts, dim=1)

@@ -1,4 +1,4 @@
-"""2-GPU check: CUDA-graph capture + replay of the sequence-parallel DiT forward (NCCL all-to-alls inside the graph).
+"""2-GPU check: segmented CUDA-graph capture + replay of the sequence-parallel DiT forward (NCCL calls eager between segments).
 Run: timeout 150 python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/sp_graph_check.py"""
 import os
 import sys
@@ -28,22 +28,12 @@ m.enable_multi_gpus_inference()
 eager = m(**kw).float()
 torch.cuda.synchronize()
 print(rank, "eager sp vs single", ((eager - single).norm() / single.norm()).item(), flush=True)
-side = torch.cuda.Stream()
-side.wait_stream(torch.cuda.current_stream())
-with torch.cuda.stream(side):
-    for _ in range(2):
-        m(**kw)
-torch.cuda.current_stream().wait_stream(side)
-torch.cuda.synchronize()
-dist.barrier()
-print(rank, "capturing", flush=True)
-g = torch.cuda.CUDAGraph()
-with torch.cuda.graph(g):
-    out = m(**kw)
-print(rank, "captured", flush=True)
-torch.cuda.synchronize()
+from stableavatar_b200.sequence_parallel import SegmentedGraph
+print(rank, "capturing segmented graph", flush=True)
+sg = SegmentedGraph(lambda: m(**kw), device=dev)
+print(rank, "captured", len(sg.segments), "segments", flush=True)
 for i in range(3):
-    g.replay()
+    out = sg.replay()
     torch.cuda.synchronize()
     print(rank, "replay", i, ((out.float() - single).norm() / single.norm()).item(), flush=True)
 dist.barrier()
