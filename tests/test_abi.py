@@ -99,3 +99,21 @@ def test_vae_from_pretrained(tmp_path):
     m = AutoencoderKLWan.from_pretrained(str(tmp_path / "vae.pth"), additional_kwargs={"spatial_compression_ratio": 8})
     assert torch.equal(m.state_dict()["model.decoder.conv1.weight"], sd["model.decoder.conv1.weight"])
     assert (m.config.latent_channels, m.config.temporal_compression_ratio, m.config.spacial_compression_ratio) == (16, 4, 8)
+
+
+def test_riflex_table_matches_reference(golden_dir):
+    """enable_riflex / disable_riflex (1B.py:891-916): the frame-axis frequency k=6 is replaced by 0.9*2*pi/L_test/scale."""
+    import numpy as np
+    from stableavatar_b200 import synth
+    from stableavatar_b200.wan_transformer3d import WanTransformer3DFantasyModel
+    g = np.load(golden_dir / "riflex.npz")
+    cfg = dict(synth.DIT_TINY, num_layers=1)
+    keys = ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim", "out_dim",
+            "num_heads", "num_layers")
+    m = WanTransformer3DFantasyModel(**{k: cfg[k] for k in keys})
+    base = m.freqs.clone()
+    m.enable_riflex()
+    assert np.allclose(m.freqs[:80].real.numpy(), g["real"], atol=1e-12) and np.allclose(m.freqs[:80].imag.numpy(), g["imag"], atol=1e-12)
+    assert not torch.equal(m.freqs, base)
+    m.disable_riflex()
+    assert torch.equal(m.freqs, base)
