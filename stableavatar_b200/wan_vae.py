@@ -94,6 +94,7 @@ class AutoencoderKLWan(nn.Module):
         self.std = torch.tensor(LATENT_STD, dtype=torch.float32)
         self.scale = [self.mean, 1.0 / self.std]
         self._prep = None
+        self._pp_group, self._pp_world, self._pp_rank = None, 1, 0
 
     @property
     def dtype(self):
@@ -211,53 +212,170 @@ class AutoencoderKLWan(nn.Module):
             ops.gemm(o, d["w_o"], d["b_o"], res=x, out=out[t].view(P, C))
         return out
 
+    # ------------------------------------------------------------------ decoder as a list of units
+    # One latent frame (chunk) flows through 20 units: conv1, middle (res, attention, res), the 15 upsample-stage modules,
+    # head. A unit owns its causal ring buffers, so a contiguous range of units can run on its own GPU: pipeline
+    # parallelism over the decoder depth keeps every op and every cache exactly as on one GPU (the caches chain through
+    # time, so the decode cannot be split along T; a W split would need a halo exchange in each of the 33 convs).
+    def _units(self):
+        p = self._prepare()
+        units = [("conv1", None), ("res", p["mid0"]), ("attn", p["attn"]), ("res", p["mid2"])]
+        units += list(p["ups"])
+        units.append(("head", None))
+        return units
+
+    def _unit_shapes(self, h, w, chunk):
+        """(frames, H, W, C) entering every unit and leaving the last one, for chunk index `chunk`."""
+        shapes, tc, H, W, C = [], 1, h, w, 32
+        for kind, d in self._units():
+            shapes.append((tc, H, W, C))
+            if kind == "conv1":
+                C = self.dims[0]
+            elif kind == "res":
+                C = d["cout"]
+            elif kind in ("up3d", "up2d"):
+                if kind == "up3d" and chunk > 0:
+                    tc *= 2
+                H, W, C = 2 * H, 2 * W, d["c"] // 2
+            elif kind == "head":
+                C = 3
+        shapes.append((tc, H, W, C))
+        return shapes
+
+    def _unit_costs(self, h, w):
+        """Relative time of every unit for a steady-state chunk: conv FLOPs divided by a per-channel-width efficiency
+        guess taken from profiles/r01_kernels_ncu.txt (narrow convs are L2-operand-bound)."""
+        costs = []
+        eff = lambda c: 0.6 if c <= 96 else (1.0 if c <= 192 else 1.1)  # noqa: E731  PFLOP/s-ish
+        for (kind, d), (tc, H, W, C) in zip(self._units(), self._unit_shapes(h, w, 1)):
+            pos = tc * H * W
+            if kind == "res":
+                f = 2 * pos * 27 * (d["cin"] * d["cout"] + d["cout"] * d["cout"]) + (2 * pos * d["cin"] * d["cout"] if "w_sc" in d else 0)
+                costs.append(f / eff(d["cout"]) + 8 * pos * d["cout"] * 40)
+            elif kind == "attn":
+                costs.append(4 * pos * pos * C + 8 * pos * C * C)
+            elif kind in ("up3d", "up2d"):
+                t2 = tc * 2 if kind == "up3d" else tc
+                f = 2 * t2 * 4 * H * W * 9 * C * (C // 2) + (2 * pos * 3 * C * 2 * C if kind == "up3d" else 0)
+                costs.append(f / eff(C // 2) + 8 * t2 * 4 * H * W * C * 40)
+            elif kind == "head":
+                costs.append(2 * pos * 27 * C * 16 / 0.3 + 8 * pos * C * 40)
+            else:
+                costs.append(2 * pos * 27 * 32 * self.dims[0])
+        return costs
+
+    @staticmethod
+    def partition_units(costs, stages):
+        """Contiguous partition of `costs` into `stages` ranges minimising the largest range sum (binary search + greedy).
+        Returns the list of (lo, hi) unit ranges, one per pipeline rank; trailing ranks may be empty."""
+        n = len(costs)
+        lo_c, hi_c = max(costs), sum(costs)
+        for _ in range(60):
+            mid = (lo_c + hi_c) / 2
+            parts, acc = 1, 0.0
+            for c in costs:
+                if acc + c > mid:
+                    parts, acc = parts + 1, c
+                else:
+                    acc += c
+            if parts <= stages:
+                hi_c = mid
+            else:
+                lo_c = mid
+        ranges, start, acc = [], 0, 0.0
+        for i, c in enumerate(costs):
+            if acc + c > hi_c * (1 + 1e-9) and i > start:
+                ranges.append((start, i))
+                start, acc = i, c
+            else:
+                acc += c
+        ranges.append((start, n))
+        while len(ranges) < stages:
+            ranges.append((n, n))
+        return ranges
+
+    def _alloc_units(self, lo, hi, h, w, dev):
+        p = self._prepare()
+        units = self._units()
+        shapes = self._unit_shapes(h, w, 1)
+        for idx in range(lo, hi):
+            kind, d = units[idx]
+            tc, H, W, _ = shapes[idx]
+            if kind == "conv1":
+                p["conv1"].alloc(1, H, W, dev)
+            elif kind == "res":
+                d["c0"].alloc(tc, H, W, dev), d["c1"].alloc(tc, H, W, dev)
+            elif kind in ("up3d", "up2d"):
+                if kind == "up3d":
+                    d["tconv"].alloc(tc, H, W, dev)
+                d["conv"].alloc(shapes[idx + 1][0], 2 * H, 2 * W, dev)
+            elif kind == "head":
+                p["head"].alloc(tc, H, W, dev)
+
+    def _run_unit(self, idx, a, chunk, video, t_out):
+        """a: [tc, H, W, C] bf16 entering unit idx for chunk `chunk` -> activation leaving it (None after the head)."""
+        p = self._prepare()
+        kind, d = self._units()[idx]
+        dev, bf = a.device, torch.bfloat16
+        tc, Hc, Wc, C = a.shape
+        if kind == "conv1":
+            p["conv1"].slot(1).copy_(a)
+            return p["conv1"].run(1, torch.empty(1, Hc, Wc, self.dims[0], device=dev, dtype=bf))
+        if kind == "res":
+            return self._res_block(d, a, tc)
+        if kind == "attn":
+            return self._attention(d, a)
+        if kind in ("up3d", "up2d"):
+            if kind == "up3d" and chunk > 0:                  # chunk 0: 'Rep' — no temporal upsampling (wan_vae.py:108-112)
+                d["tconv"].slot(tc).copy_(a)
+                a = d["tconv"].run(tc, torch.empty(2 * tc, Hc, Wc, C, device=dev, dtype=bf), out_mode=1)
+                tc *= 2
+            ops.vae_upsample2x(a, d["conv"].slot(tc))
+            return d["conv"].run(tc, torch.empty(tc, 2 * Hc, 2 * Wc, C // 2, device=dev, dtype=bf))
+        ops.vae_rmsnorm_silu(a, p["head_g"], p["head"].slot(tc))     # head
+        p["head"].run(tc, video, out_mode=2, out_T_total=video.shape[1], out_t0=t_out)
+        return None
+
     @torch.no_grad()
     def _decode_one(self, z, video):
-        """z [16, T, h, w] fp32 (one sample) -> video [3, 1 + 4 (T-1), 8h, 8w] fp32, AutoencoderKLWan_.decode :549-574."""
+        """z [16, T, h, w] fp32 (one sample) -> video [3, 1 + 4 (T-1), 8h, 8w] fp32, AutoencoderKLWan_.decode :549-574.
+        With `enable_multi_gpus_decode` each rank runs a contiguous range of units for every chunk and hands the
+        activation to the next rank (NCCL send/recv); the last rank owns the frames and broadcasts them."""
+        import torch.distributed as dist
         p = self._prepare()
         dev = z.device
         _, T, h, w = z.shape
-        bf = torch.bfloat16
-        x_all = ops.vae_latent_in(z.contiguous(), p["wc"], p["bc"], p["mean"], p["std"], 32)          # [T, h, w, 32]
-        # ring buffers sized for the steady-state chunk (1 / 2 / 4 frames per stage)
-        p["conv1"].alloc(1, h, w, dev)
-        for d in (p["mid0"], p["mid2"]):
-            d["c0"].alloc(1, h, w, dev), d["c1"].alloc(1, h, w, dev)
-        tmax, H, W = 1, h, w
-        for kind, d in p["ups"]:
-            if kind == "res":
-                d["c0"].alloc(tmax, H, W, dev), d["c1"].alloc(tmax, H, W, dev)
-            else:
-                if kind == "up3d":
-                    d["tconv"].alloc(tmax, H, W, dev)
-                    tmax *= 2
-                H, W = 2 * H, 2 * W
-                d["conv"].alloc(tmax, H, W, dev)
-        p["head"].alloc(tmax, H, W, dev)
-        n_out = video.shape[1]
+        n_units = len(self._units())
+        world, rank, group = self._pp_world, self._pp_rank, self._pp_group
+        ranges = self.partition_units(self._unit_costs(h, w), world) if world > 1 else [(0, n_units)]
+        lo, hi = ranges[rank]
+        self._alloc_units(lo, hi, h, w, dev)
+        peer = (lambda r: dist.get_global_rank(group, r) if group is not None else r)
+        last = max(r for r in range(world) if ranges[r][1] > ranges[r][0])
+        x_all = ops.vae_latent_in(z.contiguous(), p["wc"], p["bc"], p["mean"], p["std"], 32) if lo == 0 and hi > 0 else None
         t_out = 0
         for i in range(T):
-            tc = 1
-            p["conv1"].slot(1).copy_(x_all[i:i + 1])
-            a = p["conv1"].run(1, torch.empty(1, h, w, self.dims[0], device=dev, dtype=bf))
-            a = self._res_block(p["mid0"], a, 1)
-            a = self._attention(p["attn"], a)
-            a = self._res_block(p["mid2"], a, 1)
-            for kind, d in p["ups"]:
-                if kind == "res":
-                    a = self._res_block(d, a, tc)
-                    continue
-                Tc, Hc, Wc, C = a.shape
-                if kind == "up3d" and i > 0:                      # chunk 0: 'Rep' — no temporal upsampling (wan_vae.py:108-112)
-                    d["tconv"].slot(tc).copy_(a)
-                    a = d["tconv"].run(tc, torch.empty(2 * tc, Hc, Wc, C, device=dev, dtype=bf), out_mode=1)
-                    tc *= 2
-                ops.vae_upsample2x(a, d["conv"].slot(tc))
-                a = d["conv"].run(tc, torch.empty(tc, 2 * Hc, 2 * Wc, C // 2, device=dev, dtype=bf))
-            ops.vae_rmsnorm_silu(a, p["head_g"], p["head"].slot(tc))
-            p["head"].run(tc, video, out_mode=2, out_T_total=n_out, out_t0=t_out)
-            t_out += tc
-        assert t_out == n_out, (t_out, n_out)
+            shapes = self._unit_shapes(h, w, i)
+            if hi > lo:
+                if lo == 0:
+                    a = x_all[i:i + 1]
+                else:
+                    a = torch.empty(shapes[lo], device=dev, dtype=torch.bfloat16)
+                    dist.recv(a, peer(rank - 1), group=group)
+                for idx in range(lo, hi):
+                    a = self._run_unit(idx, a, i, video, t_out)
+                if hi < n_units:
+                    dist.send(a.contiguous(), peer(rank + 1), group=group)
+            t_out += shapes[n_units - 1][0]
+        assert t_out == video.shape[1], (t_out, video.shape)
+        if world > 1:
+            dist.broadcast(video, peer(last), group=group)
+
+    def enable_multi_gpus_decode(self, group=None):
+        """Pipeline-parallel decode over the ranks of `group` (default: the whole torch.distributed world). The
+        reference has no multi-GPU VAE (every rank decodes the whole clip, inference.py:574-577)."""
+        import torch.distributed as dist
+        self._pp_group, self._pp_world, self._pp_rank = group, dist.get_world_size(group), dist.get_rank(group)
 
     @torch.no_grad()
     def decode(self, z, return_dict=True):

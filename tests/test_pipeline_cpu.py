@@ -54,3 +54,18 @@ def test_overlap_weights():
     assert torch.allclose(w, torch.tensor([0.0, 0.25, 0.5, 0.75, 1.0]))
     w = overlap_weights(5, "log", "cpu", torch.float32).flatten()
     assert w[0] == 0 and abs(w[-1].item() - 1) < 1e-6 and (w[1:] > w[:-1]).all()
+
+
+def test_vae_pipeline_partition():
+    """Contiguous min-max partition used by the pipeline-parallel VAE decode."""
+    from stableavatar_b200.wan_vae import AutoencoderKLWan
+    part = AutoencoderKLWan.partition_units
+    costs = [1, 1, 1, 1, 8, 1, 1, 1, 1]
+    for stages in (1, 2, 3, 4, 9, 12):
+        r = part(costs, stages)
+        assert len(r) == stages and r[0][0] == 0
+        used = [x for x in r if x[1] > x[0]]
+        assert used[-1][1] == len(costs) and all(a[1] == b[0] for a, b in zip(used, used[1:]))
+    assert max(sum(costs[a:b]) for a, b in part(costs, 3)) == 8
+    assert max(sum(costs[a:b]) for a, b in part(costs, 2)) == 12
+    assert part([5.0], 4) == [(0, 1), (1, 1), (1, 1), (1, 1)]

@@ -72,3 +72,47 @@ def test_decode_is_idempotent_across_calls(vae):
     a = vae.decode(z).sample.clone()
     b = vae.decode(z).sample
     assert torch.equal(a, b)
+
+
+def _pp_worker(rank, world, port, q_out):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from stableavatar_b200.wan_vae import AutoencoderKLWan
+        m = AutoencoderKLWan()
+        m.load_state_dict(synth.vae_state_dict(), strict=True)
+        m = m.to(torch.device("cuda", rank))
+        z = synth.det_normal("vae_z", (1, 16, 3, 6, 8)).cuda()
+        single = m.decode(z).sample.clone()
+        m.enable_multi_gpus_decode()
+        pp = m.decode(z).sample
+        torch.cuda.synchronize()
+        q_out.put((rank, bool(torch.equal(pp, single))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_pipeline_parallel_decode_equals_single_gpu(world):
+    """Depth-pipelined multi-GPU decode: same ops, same caches -> bit-identical frames on every rank."""
+    import socket
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert all(res.values()), res
