@@ -172,6 +172,13 @@ int sa_cfg_euler_step(const void* pred, const void* latents, void* out, void* no
  *   out_mode 0: out bf16 [Tout,H,W,Cout] = acc + bias (+ res, same layout: the x + h of :223)
  *   out_mode 1: Cout = 2C; channel n of frame t goes to frame 2t + n/C, channel n%C of bf16 [2*Tout,H,W,C] (:137-140)
  *   out_mode 2: out f32 planar [Cout, out_T_total, H, W] at frame out_t0 + t, clamped to [-1, 1] (:668)
+ *   out_mode 3: out f32 channels-last [Tout,H,W,Cout], unclamped (Encoder3d.head, :320-322)
+ * Encode side (Encoder3d :268-369, Resample downsample2d/3d :95-105, 145-162): pad_h / pad_w = zero rows / columns in
+ * front of H / W (negative = KH/2, KW/2, the 'same' padding; the back padding is whatever the taps reach, zero filled;
+ * output H x W always equals input H x W); stride_t = temporal stride (0 = 1), `in` then holds (Tout-1)*stride_t + KT
+ * frames. ZeroPad2d(0,1,0,1) + Conv2d(3, stride 2) (:96-98) is run as KH = KW = 2, pad 0 over the space-to-depth
+ * input of sa_vae_space_to_depth with the 3x3 weights scattered into the 2x2x(4C) taps; time_conv stride (2,1,1)
+ * (:103-104) is KT = 3, stride_t = 2.
  */
 typedef struct {
   const void* in;
@@ -181,6 +188,7 @@ typedef struct {
   void* out;
   int32_t Tout, H, W, Cin, Cout, KT, KH, KW;
   int32_t out_mode, out_T_total, out_t0;
+  int32_t pad_h, pad_w, stride_t;
 } sa_conv_args;
 int sa_conv3d_cl(const sa_conv_args* args, sa_stream_t stream);
 
@@ -196,6 +204,19 @@ int sa_softmax_rows(const void* in, void* out, int32_t rows, int32_t n, int64_t 
  * bf16 [P, Cpad] channels-last, channels >= Cz zero. wc f32 [Cz, Cz], bc/mean/stdv f32 [Cz]. */
 int sa_vae_latent_in(const void* z, const void* wc, const void* bc, const void* mean, const void* stdv, void* out,
                      int32_t Cz, int64_t P, int32_t Cpad, sa_stream_t stream);
+
+
+/* ---- Wan VAE encode helpers (wan/models/wan_vae.py:519-547) -------------------------------------------------------
+ * out[t, y, x, (dy*2 + dx)*C + c] = in[t, 2y + dy, 2x + dx, c]: bf16 [T,H,W,C] -> [T,H/2,W/2,4C] (H, W even), the input
+ * layout of the stride-2 Conv2d of Resample('downsample2d'/'downsample3d') (:96-104). */
+int sa_vae_space_to_depth(const void* in, void* out, int32_t T, int32_t H, int32_t W, int32_t C, sa_stream_t stream);
+/* Video in: x f32 planar [Cx, P] (P = T*H*W positions of one sample) -> bf16 channels-last [P, Cpad], channels >= Cx
+ * zero: the input of Encoder3d.conv1 (:291). */
+int sa_vae_video_in(const void* x, void* out, int32_t Cx, int64_t P, int32_t Cpad, sa_stream_t stream);
+/* Latent out: h f32 channels-last [P, 2*Cz] (Encoder3d.head output) -> conv1 (1x1x1, wc f32 [2Cz, 2Cz], bc f32 [2Cz])
+ * -> out f32 planar [2*Cz, P]: channels [0,Cz) = (mu - mean) / stdv, channels [Cz,2Cz) = log-variance (:539-545). */
+int sa_vae_latent_out(const void* h, const void* wc, const void* bc, const void* mean, const void* stdv, void* out,
+                      int32_t Cz, int64_t P, sa_stream_t stream);
 
 #ifdef __cplusplus
 }

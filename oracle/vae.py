@@ -1,10 +1,12 @@
-"""ORACLE (test infrastructure, not product code) — CPU restatement of the Wan causal-3D VAE decode.
+"""ORACLE (test infrastructure, not product code) — CPU restatement of the Wan causal-3D VAE decode and encode.
 
 Plain PyTorch fp32 on CPU over a reference-named state dict (keys as AutoencoderKLWan.state_dict(): "model.decoder...",
 "model.conv2..."). Restates wan/models/wan_vae.py: CausalConv3d :20-39, RMS_norm :42-57, Resample(upsample2d/3d)
 :69-143, ResidualBlock :189-223, AttentionBlock :226-265, Decoder3d :372-475, AutoencoderKLWan_.decode :549-574,
 AutoencoderKLWan.decode :666-681. The per-conv causal feature cache is kept explicitly per conv index, exactly in the
 order the reference's feat_idx counter walks the modules. Pinned by tests/golden/vae_tiny.npz (real reference output).
+The encode side (Encoder3d :268-369, Resample(downsample2d/3d) :95-105, 145-162, AutoencoderKLWan_.encode :519-547,
+AutoencoderKLWan.encode :649-664) is restated the same way and pinned by tests/golden/vae_enc_tiny.npz.
 """
 from __future__ import annotations
 
@@ -155,4 +157,85 @@ def vae_decode(sd, z, dim=96, dim_mult=(1, 2, 4, 4), hooks=None):
                 hooks.setdefault("chunks", []).append(o)
             frames.append(o)
         outs.append(torch.cat(frames, dim=2).clamp_(-1, 1).squeeze(0))
+    return torch.stack(outs)
+
+
+# ------------------------------------------------------------------------------------------------------ encode
+def encoder_layout(dim=96, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_downsample=(False, True, True)):
+    """Module list of Encoder3d.downsamples (vae.py:294-310): ('res', cin, cout) / ('down3d'|'down2d', c)."""
+    dims = [dim * u for u in [1] + list(dim_mult)]
+    mods = []
+    for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+        for _ in range(num_res_blocks):
+            mods.append(("res", cin, cout))
+            cin = cout
+        if i != len(dim_mult) - 1:
+            mods.append(("down3d" if temperal_downsample[i] else "down2d", cout))
+    return dims, mods
+
+
+def resample_down(sd, pre, x, fc, mode):
+    """vae.py:145-162 — ZeroPad2d(right 1, bottom 1) + Conv2d 3x3 stride 2 per frame; downsample3d then applies a
+    (3,1,1) stride-(2,1,1) conv over [last frame of the previous chunk, x] — except on the first chunk, whose frame
+    passes through untouched and only seeds the cache."""
+    b, c, t, h, w = x.shape
+    y = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+    y = F.conv2d(F.pad(y, (0, 1, 0, 1)), sd[pre + "resample.1.weight"], sd[pre + "resample.1.bias"], stride=2)
+    x = y.view(b, t, c, y.shape[-2], y.shape[-1]).permute(0, 2, 1, 3, 4)
+    if mode == "down3d":
+        idx = fc.idx
+        if fc.map[idx] is None:
+            fc.map[idx] = x.clone()
+        else:
+            cache_x = x[:, :, -1:].clone()
+            x = F.conv3d(torch.cat([fc.map[idx][:, :, -1:], x], 2), sd[pre + "time_conv.weight"],
+                         sd[pre + "time_conv.bias"], stride=(2, 1, 1))
+            fc.map[idx] = cache_x
+        fc.idx += 1
+    return x
+
+
+def encoder_chunk(sd, x, fc, mods, pre="model.encoder."):
+    """Encoder3d.forward (vae.py:324-369) on one chunk of frames (1 for the first chunk, then 4)."""
+    fc.idx = 0
+    x = _cached_conv(sd, pre + "conv1", x, fc)
+    for i, m in enumerate(mods):
+        p = f"{pre}downsamples.{i}."
+        if m[0] == "res":
+            x = residual_block(sd, p, x, fc, m[1] != m[2])
+        else:
+            x = resample_down(sd, p, x, fc, m[0])
+    x = residual_block(sd, pre + "middle.0.", x, fc, False)
+    x = attention_block(sd, pre + "middle.1.", x)
+    x = residual_block(sd, pre + "middle.2.", x, fc, False)
+    x = F.silu(rms_norm(x, sd[pre + "head.0.gamma"]))
+    return _cached_conv(sd, pre + "head.2", x, fc)
+
+
+def count_cached_convs_enc(mods):
+    return 1 + sum(2 if m[0] == "res" else (1 if m[0] == "down3d" else 0) for m in mods) + 4 + 1
+
+
+def vae_encode(sd, x, dim=96, dim_mult=(1, 2, 4, 4), hooks=None):
+    """AutoencoderKLWan._encode (vae.py:642-647) for x [B, 3, T, H, W] -> [B, 32, 1 + (T-1)//4, H/8, W/8]: channels
+    [0,16) the normalised mean (what DiagonalGaussianDistribution.mode() returns), [16,32) the raw log-variance."""
+    _, mods = encoder_layout(dim, dim_mult)
+    zc = sd["model.conv1.weight"].shape[0] // 2
+    mean = torch.tensor(LATENT_MEAN[:zc]).view(1, -1, 1, 1, 1)
+    inv_std = (1.0 / torch.tensor(LATENT_STD[:zc])).view(1, -1, 1, 1, 1)
+    outs = []
+    for u in x:
+        u = u.unsqueeze(0)
+        fc = _Cache(count_cached_convs_enc(mods))
+        chunks = []
+        for i in range(1 + (u.shape[2] - 1) // 4):                                   # vae.py:523-538: 1, 4, 4, ...
+            frames = u[:, :, :1] if i == 0 else u[:, :, 1 + 4 * (i - 1):1 + 4 * i]
+            o = encoder_chunk(sd, frames, fc, mods)
+            if hooks is not None:
+                hooks.setdefault("chunks", []).append(o)
+            chunks.append(o)
+        out = torch.cat(chunks, dim=2)
+        mu, log_var = causal_conv3d(out, sd["model.conv1.weight"], sd["model.conv1.bias"], None).chunk(2, dim=1)
+        mu = (mu - mean) * inv_std                                                    # vae.py:540-542
+        outs.append(torch.cat([mu, log_var], dim=1).squeeze(0))
     return torch.stack(outs)

@@ -1,6 +1,9 @@
 // conv3d_tcgen05.cu — causal 3-D convolution of the Wan VAE decoder as an implicit GEMM on tcgen05 tensor cores.
 //
-//   out[t, h, w, n] = bias[n] + sum_{kt,kh,kw,c} in[t + kt, h + kh - KH/2, w + kw - KW/2, c] * Wt[n, (kt,kh,kw,c)]
+//   out[t, h, w, n] = bias[n] + sum_{kt,kh,kw,c} in[t*stride_t + kt, h + kh - pad_h, w + kw - pad_w, c] * Wt[n, (kt,kh,kw,c)]
+//
+// (pad = K/2 'same' for the decoder; the encoder's stride-2 3x3 Conv2d runs as a 2x2-tap conv with pad 0 over a
+// space-to-depth input, and its (3,1,1) stride-2 time conv uses stride_t = 2.)
 //
 // Activations are channels-last bf16 [T, H, W, C]; `in` already carries the KT-1 causal cache frames in front
 // (ring buffer kept by the host, replacing the reference's per-chunk clone + cat: wan/models/wan_vae.py:31-39,
@@ -41,6 +44,7 @@ struct Params {
   int bn, ksub, groups_per_tap, stages, stage_bytes;
   int tiles_w, tiles_h, tiles_n;
   int out_mode, out_T_total, out_t0;
+  int pad_h, pad_w, stride_t;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -113,7 +117,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
           uint8_t* st = smem + s * p.stage_bytes;
           for (int j = 0; j < p.ksub; ++j) {
             const int c0 = (grp * p.ksub + j) * SUBK;
-            tma_load_4d(st + j * A_SUB_BYTES, &tmap_in, &full[s], c0, w0 + kw - p.KW / 2, h0 + kh - p.KH / 2, t + kt);
+            tma_load_4d(st + j * A_SUB_BYTES, &tmap_in, &full[s], c0, w0 + kw - p.pad_w, h0 + kh - p.pad_h, t * p.stride_t + kt);
             tma_load_2d(st + p.ksub * A_SUB_BYTES + j * b_sub_bytes, &tmap_w, &full[s], tap * p.Cin + c0, nt * p.bn);
           }
         }
@@ -177,7 +181,12 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
         float y[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(rr[i]) + (n0 + i < p.Cout ? __ldg(p.bias + n0 + i) : 0.f);
-        if (p.out_mode == 2) {  // fp32 planar [Cout, T_total, H, W], clamped to [-1, 1] (wan_vae.py:668)
+        if (p.out_mode == 3) {  // fp32 channels-last [Tout, H, W, Cout], unclamped (encoder head, wan_vae.py:320-322)
+          float* o = reinterpret_cast<float*>(p.out) + pos * p.Cout + n0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + i < p.Cout) o[i] = y[i];
+        } else if (p.out_mode == 2) {  // fp32 planar [Cout, T_total, H, W], clamped to [-1, 1] (wan_vae.py:668)
           float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
@@ -236,8 +245,8 @@ extern "C" int sa_conv3d_cl(const sa_conv_args* a, sa_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!a || !a->in || !a->w || !a->bias || !a->out) { set_error("sa_conv3d_cl: null pointer"); return SA_ERR_BAD_ARG; }
   if (a->Tout <= 0 || a->H <= 0 || a->W <= 0 || a->Cin <= 0 || a->Cout <= 0 || a->KT <= 0 || a->KH <= 0 || a->KW <= 0 ||
-      !(a->KH & 1) || !(a->KW & 1)) {
-    set_error("sa_conv3d_cl: bad dims (odd KH/KW required)");
+      a->pad_h >= a->KH || a->pad_w >= a->KW || a->stride_t < 0) {
+    set_error("sa_conv3d_cl: bad dims / padding / stride");
     return SA_ERR_BAD_ARG;
   }
   if (a->Cin % SUBK) { set_error("sa_conv3d_cl: Cin must be a multiple of 32 (pad on the host), got %d", a->Cin); return SA_ERR_BAD_ARG; }
@@ -247,8 +256,8 @@ extern "C" int sa_conv3d_cl(const sa_conv_args* a, sa_stream_t stream_) {
   else if (cout_pad <= MAX_BN) bn = cout_pad;
   else if (cout_pad % 128 == 0) bn = 128;
   else { set_error("sa_conv3d_cl: unsupported Cout %d", a->Cout); return SA_ERR_UNSUPPORTED; }
-  if (a->out_mode < 0 || a->out_mode > 2 || (a->out_mode != 2 && a->Cout % 16) || (a->out_mode == 1 && (a->Cout / 2) % 16) ||
-      (a->res && a->out_mode == 2)) {
+  if (a->out_mode < 0 || a->out_mode > 3 || (a->out_mode < 2 && a->Cout % 16) || (a->out_mode == 1 && (a->Cout / 2) % 16) ||
+      (a->res && a->out_mode >= 2)) {
     set_error("sa_conv3d_cl: bad out_mode / Cout combination");
     return SA_ERR_BAD_ARG;
   }
@@ -265,10 +274,13 @@ extern "C" int sa_conv3d_cl(const sa_conv_args* a, sa_stream_t stream_) {
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.tiles_w = (a->W + TW - 1) / TW; p.tiles_h = (a->H + TH - 1) / TH; p.tiles_n = cout_pad / bn;
   p.out_mode = a->out_mode; p.out_T_total = a->out_T_total; p.out_t0 = a->out_t0;
+  p.pad_h = a->pad_h < 0 ? a->KH / 2 : a->pad_h;
+  p.pad_w = a->pad_w < 0 ? a->KW / 2 : a->pad_w;
+  p.stride_t = a->stride_t > 0 ? a->stride_t : 1;
 
   CUtensorMap tin, tw;
   {
-    const int Tin = a->Tout + a->KT - 1;
+    const int Tin = (a->Tout - 1) * p.stride_t + a->KT;
     uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)Tin};
     uint64_t strides[3] = {(uint64_t)a->Cin * 2, (uint64_t)a->W * a->Cin * 2, (uint64_t)a->H * a->W * a->Cin * 2};
     uint32_t box[4] = {SUBK, TW, TH, 1};

@@ -1,6 +1,8 @@
 // vae_kernels.cu — the HBM-bound kernels of the Wan VAE decoder, all on channels-last bf16 activations [P, C]:
 // channel RMS-norm (+SiLU) (wan_vae.py:54-57 + nn.SiLU), nearest-exact 2x upsample (:60-66, 79-88), row softmax of the
-// single-head middle attention (:243-265), and the latent de-normalisation + 1x1x1 conv2 (:552-559).
+// single-head middle attention (:243-265), and the latent de-normalisation + 1x1x1 conv2 (:552-559). Encode side:
+// space-to-depth in front of the stride-2 Conv2d (:96-104), video-in layout change, 1x1x1 conv1 + latent normalisation
+// (:539-545).
 #include "../../include/stableavatar_b200.h"
 #include "sa_host.h"
 #include "sa_ptx.cuh"
@@ -121,6 +123,47 @@ __global__ void latent_in_kernel(const float* z, const float* wc, const float* b
   }
 }
 
+// ------------------------------------------------------------------------------------------------ encode helpers
+// out[t, y, x, (dy*2+dx)*C + c] = in[t, 2y+dy, 2x+dx, c]; one 16-byte chunk (8 channels) per thread, writes coalesced.
+__global__ void space_to_depth_kernel(const uint4* in, uint4* out, int T, int H, int W, int C8) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)T * Ho * Wo * 4 * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % C8;
+    long long r = i / C8;
+    const int d = r % 4;
+    r /= 4;
+    const int x = r % Wo;
+    r /= Wo;
+    const int y = r % Ho;
+    const int t = r / Ho;
+    out[i] = in[(((long long)t * H + 2 * y + (d >> 1)) * W + 2 * x + (d & 1)) * C8 + c];
+  }
+}
+
+// x f32 planar [Cx, P] -> bf16 channels-last [P, Cpad] (zero padded channels).
+__global__ void video_in_kernel(const float* x, __nv_bfloat16* out, int Cx, long long P, int Cpad) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P * Cpad; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % Cpad;
+    const long long pos = i / Cpad;
+    out[i] = __float2bfloat16_rn(c < Cx ? x[(long long)c * P + pos] : 0.f);
+  }
+}
+
+// out[co, pos] = b[co] + sum_ci Wc[co, ci] * h[pos, ci]; co < Cz additionally (. - mean[co]) / std[co].
+__global__ void latent_out_kernel(const float* h, const float* wc, const float* bc, const float* mean, const float* stdv,
+                                  float* out, int Cz, long long P) {
+  const int C2 = 2 * Cz;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P * C2; i += (long long)gridDim.x * blockDim.x) {
+    const long long pos = i % P;
+    const int co = i / P;
+    float acc = bc[co];
+    for (int ci = 0; ci < C2; ++ci) acc = fmaf(wc[co * C2 + ci], h[pos * C2 + ci], acc);
+    if (co < Cz) acc = (acc - mean[co]) * (1.0f / stdv[co]);
+    out[i] = acc;
+  }
+}
+
 static inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 32;
@@ -186,5 +229,37 @@ extern "C" int sa_vae_latent_in(const void* z, const void* wc, const void* bc, c
       reinterpret_cast<const float*>(z), reinterpret_cast<const float*>(wc), reinterpret_cast<const float*>(bc),
       reinterpret_cast<const float*>(mean), reinterpret_cast<const float*>(stdv), reinterpret_cast<__nv_bfloat16*>(out), Cz, P, Cpad);
   SA_LAUNCH_CHECK("latent_in_kernel launch");
+  return SA_OK;
+}
+
+extern "C" int sa_vae_space_to_depth(const void* in, void* out, int32_t T, int32_t H, int32_t W, int32_t C, sa_stream_t stream) {
+  using namespace sa;
+  if (!in || !out || T <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || (H & 1) || (W & 1)) {
+    set_error("sa_vae_space_to_depth: bad argument (C %% 8 == 0, H and W even)");
+    return SA_ERR_BAD_ARG;
+  }
+  vae::space_to_depth_kernel<<<vae::grid_for((long long)T * H * W * (C / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), T, H, W, C / 8);
+  SA_LAUNCH_CHECK("space_to_depth_kernel launch");
+  return SA_OK;
+}
+
+extern "C" int sa_vae_video_in(const void* x, void* out, int32_t Cx, int64_t P, int32_t Cpad, sa_stream_t stream) {
+  using namespace sa;
+  if (!x || !out || Cx <= 0 || P <= 0 || Cpad < Cx) { set_error("sa_vae_video_in: bad argument"); return SA_ERR_BAD_ARG; }
+  vae::video_in_kernel<<<vae::grid_for(P * Cpad), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float*>(x), reinterpret_cast<__nv_bfloat16*>(out), Cx, P, Cpad);
+  SA_LAUNCH_CHECK("video_in_kernel launch");
+  return SA_OK;
+}
+
+extern "C" int sa_vae_latent_out(const void* h, const void* wc, const void* bc, const void* mean, const void* stdv, void* out,
+                                 int32_t Cz, int64_t P, sa_stream_t stream) {
+  using namespace sa;
+  if (!h || !wc || !bc || !mean || !stdv || !out || Cz <= 0 || P <= 0) { set_error("sa_vae_latent_out: bad argument"); return SA_ERR_BAD_ARG; }
+  vae::latent_out_kernel<<<vae::grid_for(P * 2 * Cz), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float*>(h), reinterpret_cast<const float*>(wc), reinterpret_cast<const float*>(bc),
+      reinterpret_cast<const float*>(mean), reinterpret_cast<const float*>(stdv), reinterpret_cast<float*>(out), Cz, P);
+  SA_LAUNCH_CHECK("latent_out_kernel launch");
   return SA_OK;
 }

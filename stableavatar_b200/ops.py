@@ -224,18 +224,21 @@ class ConvArgs(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("out", C.c_void_p),
                 ("Tout", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
                 ("KT", C.c_int32), ("KH", C.c_int32), ("KW", C.c_int32),
-                ("out_mode", C.c_int32), ("out_T_total", C.c_int32), ("out_t0", C.c_int32)]
+                ("out_mode", C.c_int32), ("out_T_total", C.c_int32), ("out_t0", C.c_int32),
+                ("pad_h", C.c_int32), ("pad_w", C.c_int32), ("stride_t", C.c_int32)]
 
 
-def conv3d_cl(x, w, bias, *, cout, k, out, res=None, out_mode=0, out_T_total=0, out_t0=0):
-    """Causal conv on channels-last bf16 x [Tout + KT - 1, H, W, Cin] (leading frames = cache) — sa_conv3d_cl."""
+def conv3d_cl(x, w, bias, *, cout, k, out, res=None, out_mode=0, out_T_total=0, out_t0=0, pad=None, stride_t=1):
+    """Causal conv on channels-last bf16 x [(Tout-1)*stride_t + KT, H, W, Cin] (leading frames = cache) — sa_conv3d_cl.
+    pad = (front pad H, front pad W), default 'same' (K // 2)."""
     _need_cuda(x, w)
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and w.dtype == torch.bfloat16 and w.is_contiguous()
     assert bias.dtype == torch.float32 and out.is_contiguous() and (res is None or (res.is_contiguous() and res.dtype == torch.bfloat16))
     Tin, H, W, Cin = x.shape
     a = ConvArgs(inp=x.data_ptr(), w=w.data_ptr(), bias=bias.data_ptr(), res=L.ptr(res), out=out.data_ptr(),
-                 Tout=Tin - k[0] + 1, H=H, W=W, Cin=Cin, Cout=cout, KT=k[0], KH=k[1], KW=k[2], out_mode=out_mode,
-                 out_T_total=out_T_total, out_t0=out_t0)
+                 Tout=(Tin - k[0]) // stride_t + 1, H=H, W=W, Cin=Cin, Cout=cout, KT=k[0], KH=k[1], KW=k[2],
+                 out_mode=out_mode, out_T_total=out_T_total, out_t0=out_t0, pad_h=-1 if pad is None else pad[0],
+                 pad_w=-1 if pad is None else pad[1], stride_t=stride_t)
     L.check(L.lib().sa_conv3d_cl(C.byref(a), L.stream_ptr()), "sa_conv3d_cl")
     return out
 
@@ -287,4 +290,37 @@ def vae_latent_in(z, wc, bc, mean, std, cpad):
     L.check(L.lib().sa_vae_latent_in(C.c_void_p(z.data_ptr()), C.c_void_p(wc.data_ptr()), C.c_void_p(bc.data_ptr()),
                                      C.c_void_p(mean.data_ptr()), C.c_void_p(std.data_ptr()), C.c_void_p(out.data_ptr()),
                                      Cz, C.c_int64(P), cpad, L.stream_ptr()), "sa_vae_latent_in")
+    return out
+
+
+def vae_space_to_depth(x, out):
+    """bf16 [T, H, W, C] -> [T, H/2, W/2, 4C] with channel (dy*2 + dx)*C + c — sa_vae_space_to_depth."""
+    _need_cuda(x)
+    T, H, W, Cc = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and out.shape == (T, H // 2, W // 2, 4 * Cc) and x.dtype == out.dtype == torch.bfloat16
+    L.check(L.lib().sa_vae_space_to_depth(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), T, H, W, Cc, L.stream_ptr()),
+            "sa_vae_space_to_depth")
+    return out
+
+
+def vae_video_in(x, cpad):
+    """f32 planar [Cx, T, H, W] -> bf16 channels-last [T, H, W, cpad] — sa_vae_video_in."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    Cx = x.shape[0]
+    out = torch.empty(*x.shape[1:], cpad, device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().sa_vae_video_in(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), Cx, C.c_int64(x.numel() // Cx), cpad,
+                                    L.stream_ptr()), "sa_vae_video_in")
+    return out
+
+
+def vae_latent_out(h, wc, bc, mean, std, out):
+    """f32 channels-last h [T, H, W, 2Cz] -> f32 planar out [2Cz, T, H, W] (conv1 + latent normalisation) — sa_vae_latent_out."""
+    _need_cuda(h)
+    C2 = h.shape[-1]
+    assert h.dtype == torch.float32 and h.is_contiguous() and out.dtype == torch.float32 and out.is_contiguous()
+    assert out.numel() == h.numel() and wc.numel() == C2 * C2
+    L.check(L.lib().sa_vae_latent_out(C.c_void_p(h.data_ptr()), C.c_void_p(wc.data_ptr()), C.c_void_p(bc.data_ptr()),
+                                      C.c_void_p(mean.data_ptr()), C.c_void_p(std.data_ptr()), C.c_void_p(out.data_ptr()),
+                                      C2 // 2, C.c_int64(h.numel() // C2), L.stream_ptr()), "sa_vae_latent_out")
     return out

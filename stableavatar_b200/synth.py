@@ -203,5 +203,68 @@ def vae_decoder_param_shapes(dim=96, z_dim=16, dim_mult=(1, 2, 4, 4)):
     return s
 
 
-def vae_state_dict(seed: int = 0, **kw) -> dict:
-    return fill_state_dict(vae_decoder_param_shapes(**kw), seed)
+def vae_encoder_layout(dim=96, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_downsample=(False, True, True)):
+    """Module list of Encoder3d.downsamples (wan/models/wan_vae.py:294-310): ('res', cin, cout) / ('down3d'|'down2d', c)."""
+    dims = [dim * u for u in [1] + list(dim_mult)]
+    mods = []
+    for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+        for _ in range(num_res_blocks):
+            mods.append(("res", cin, cout))
+            cin = cout
+        if i != len(dim_mult) - 1:
+            mods.append(("down3d" if temperal_downsample[i] else "down2d", cout))
+    return dims, mods
+
+
+def vae_encoder_param_shapes(dim=96, z_dim=16, dim_mult=(1, 2, 4, 4)):
+    """Names/shapes of the encode-side parameters of AutoencoderKLWan (wan/models/wan_vae.py:268-322, 515), checked
+    against the real module by tools/gen_golden_vae.py."""
+    dims, mods = vae_encoder_layout(dim, dim_mult)
+    s = {"model.conv1.weight": (2 * z_dim, 2 * z_dim, 1, 1, 1), "model.conv1.bias": (2 * z_dim,)}
+    p = "model.encoder."
+    s[p + "conv1.weight"] = (dims[0], 3, 3, 3, 3)
+    s[p + "conv1.bias"] = (dims[0],)
+
+    def res(pre, cin, cout):
+        s[pre + "residual.0.gamma"] = (cin, 1, 1, 1)
+        s[pre + "residual.2.weight"] = (cout, cin, 3, 3, 3)
+        s[pre + "residual.2.bias"] = (cout,)
+        s[pre + "residual.3.gamma"] = (cout, 1, 1, 1)
+        s[pre + "residual.6.weight"] = (cout, cout, 3, 3, 3)
+        s[pre + "residual.6.bias"] = (cout,)
+        if cin != cout:
+            s[pre + "shortcut.weight"] = (cout, cin, 1, 1, 1)
+            s[pre + "shortcut.bias"] = (cout,)
+
+    for i, m in enumerate(mods):
+        q = f"{p}downsamples.{i}."
+        if m[0] == "res":
+            res(q, m[1], m[2])
+        else:
+            c = m[1]
+            s[q + "resample.1.weight"] = (c, c, 3, 3)
+            s[q + "resample.1.bias"] = (c,)
+            if m[0] == "down3d":
+                s[q + "time_conv.weight"] = (c, c, 3, 1, 1)
+                s[q + "time_conv.bias"] = (c,)
+    c = dims[-1]
+    res(p + "middle.0.", c, c)
+    s[p + "middle.1.norm.gamma"] = (c, 1, 1)
+    s[p + "middle.1.to_qkv.weight"] = (3 * c, c, 1, 1)
+    s[p + "middle.1.to_qkv.bias"] = (3 * c,)
+    s[p + "middle.1.proj.weight"] = (c, c, 1, 1)
+    s[p + "middle.1.proj.bias"] = (c,)
+    res(p + "middle.2.", c, c)
+    s[p + "head.0.gamma"] = (c, 1, 1, 1)
+    s[p + "head.2.weight"] = (2 * z_dim, c, 3, 3, 3)
+    s[p + "head.2.bias"] = (2 * z_dim,)
+    return s
+
+
+def vae_state_dict(seed: int = 0, encoder: bool = False, **kw) -> dict:
+    """Decoder-side state dict; with encoder=True the encoder + conv1 parameters too (values are seeded per name, so
+    the decoder tensors are the same either way)."""
+    shapes = dict(vae_decoder_param_shapes(**kw))
+    if encoder:
+        shapes.update(vae_encoder_param_shapes(**kw))
+    return fill_state_dict(shapes, seed)

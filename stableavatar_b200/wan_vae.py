@@ -1,9 +1,11 @@
-"""Wan causal-3D VAE decode on hand-written sm_100a kernels.
+"""Wan causal-3D VAE decode and encode on hand-written sm_100a kernels.
 
-Drop-in for the decode side of `AutoencoderKLWan` (wan/models/wan_vae.py:619-704): same constructor arguments,
+Drop-in for `AutoencoderKLWan` (wan/models/wan_vae.py:619-704): same constructor arguments,
 `.config.{latent_channels, temporal_compression_ratio, spacial_compression_ratio}`, the reference's state-dict key
-names (`model.decoder...`, `model.conv2...`; encoder keys are accepted and ignored), and
-`decode(z, return_dict=True) -> DecoderOutput(.sample)` with z [B,16,T,h,w] -> [B,3,1+4(T-1),8h,8w] fp32 in [-1,1].
+names (`model.decoder...`, `model.conv2...`, `model.encoder...`, `model.conv1...`),
+`decode(z, return_dict=True) -> DecoderOutput(.sample)` with z [B,16,T,h,w] -> [B,3,1+4(T-1),8h,8w] fp32 in [-1,1], and
+`encode(x, return_dict=True) -> AutoencoderKLOutput(.latent_dist)` with x [B,3,T,H,W] -> a diagonal Gaussian over
+[B,16,1+(T-1)//4,H/8,W/8] whose `.mode()` is what the pipeline consumes (pipe.py:402-403).
 
 Internals are B200-first rather than a transcription of Decoder3d.forward (:426-475): activations are channels-last
 bf16, every 3x3x3 causal conv is an implicit GEMM on tcgen05 fed by TMA (ops.conv3d_cl), and the 33-entry feature cache
@@ -11,8 +13,9 @@ bf16, every 3x3x3 causal conv is an implicit GEMM on tcgen05 fed by TMA (ops.con
 two leading frames are the cache: the producer of a conv's input writes straight behind them. Chunking follows the
 reference exactly (one latent frame per chunk, chunk 0 skips the temporal upsamplers and yields a single frame).
 
-`encode` is outside the hot path and is not implemented here: pass the reference's VAE, or
-pre-encoded conditioning latents, to the pipeline for that one call.
+`encode` (the conditioning clip) reuses the same kernels: chunks of 1, 4, 4, ... frames
+(:523-538); the stride-2 Conv2d of Resample('downsample*') runs as a 2x2-tap conv over a space-to-depth copy, the
+stride-(2,1,1) time_conv as the same implicit GEMM with a temporal stride over a one-frame ring buffer.
 """
 from __future__ import annotations
 
@@ -22,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .synth import vae_decoder_layout, vae_decoder_param_shapes
+from .synth import vae_decoder_layout, vae_decoder_param_shapes, vae_encoder_layout, vae_encoder_param_shapes
 
 LATENT_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508, 0.4134, -0.0715, 0.5517, -0.3632,
                -0.1922, -0.9497, 0.2503, -0.2921]
@@ -33,6 +36,31 @@ LATENT_STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743, 3.
 class DecoderOutput:
     def __init__(self, sample):
         self.sample = sample
+
+
+class DiagonalGaussianDistribution:
+    """The slice of diffusers' class the reference uses on the encode result (wan_vae.py:655; pipe.py:402-403)."""
+
+    def __init__(self, parameters):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std, self.var = torch.exp(0.5 * self.logvar), torch.exp(self.logvar)
+
+    def mode(self):
+        return self.mean
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+
+class AutoencoderKLOutput:
+    def __init__(self, latent_dist):
+        self.latent_dist = latent_dist
+
+    def __getitem__(self, i):
+        return (self.latent_dist,)[i]
 
 
 def _build_param_tree(root: nn.Module, shapes: dict):
@@ -49,10 +77,12 @@ def _build_param_tree(root: nn.Module, shapes: dict):
 class _Conv:
     """One causal conv with its persistent input ring buffer [2 + Tmax, H, W, Cin] (two leading cache frames)."""
 
-    def __init__(self, weight, bias, dev):
+    def __init__(self, weight, bias, dev, lead=None, stride_t=1, pad=None):
         if weight.dim() == 4:
             weight = weight.unsqueeze(2)
         cout, cin, kt, kh, kw = weight.shape
+        self.lead = kt - 1 if lead is None else lead           # cache frames kept in front of the chunk
+        self.stride_t, self.pad = stride_t, pad
         self.cout, self.cin, self.k = cout, (cin + 31) // 32 * 32, (kt, kh, kw)
         cout_pad = (cout + 15) // 16 * 16
         w = torch.zeros(cout_pad, kt, kh, kw, self.cin, device=dev, dtype=torch.float32)
@@ -62,7 +92,7 @@ class _Conv:
         self.buf = None
 
     def alloc(self, tmax, H, W, dev):
-        lead = self.k[0] - 1
+        lead = self.lead
         if self.buf is None or self.buf.shape != (lead + tmax, H, W, self.cin):
             self.buf = torch.zeros(lead + tmax, H, W, self.cin, device=dev, dtype=torch.bfloat16)
         else:
@@ -71,12 +101,13 @@ class _Conv:
 
     def slot(self, tc):
         """Where the producer writes this chunk's `tc` input frames."""
-        lead = self.k[0] - 1
+        lead = self.lead
         return self.buf[lead:lead + tc]
 
     def run(self, tc, out, res=None, keep_cache=True, **kw):
-        lead = self.k[0] - 1
-        ops.conv3d_cl(self.buf[:lead + tc], self.w, self.bias, cout=self.cout, k=self.k, out=out, res=res, **kw)
+        lead = self.lead
+        ops.conv3d_cl(self.buf[:lead + tc], self.w, self.bias, cout=self.cout, k=self.k, out=out, res=res, pad=self.pad,
+                      stride_t=self.stride_t, **kw)
         if keep_cache and lead:                      # new cache = last two frames of [old cache, x]  (wan_vae.py:208-220)
             for j in range(lead):
                 self.buf[j].copy_(self.buf[tc + j])
@@ -90,10 +121,13 @@ class AutoencoderKLWan(nn.Module):
                                       spacial_compression_ratio=spacial_compression_ratio)
         self.dims, self.mods = vae_decoder_layout()
         _build_param_tree(self, vae_decoder_param_shapes(z_dim=latent_channels))
+        self.enc_dims, self.enc_mods = vae_encoder_layout()
+        _build_param_tree(self, vae_encoder_param_shapes(z_dim=latent_channels))
+        self._has_encoder = False          # set by load_state_dict / init when encoder weights are actually present
         self.mean = torch.tensor(LATENT_MEAN, dtype=torch.float32)
         self.std = torch.tensor(LATENT_STD, dtype=torch.float32)
         self.scale = [self.mean, 1.0 / self.std]
-        self._prep = None
+        self._prep = self._prep_enc = None
         self._pp_group, self._pp_world, self._pp_rank = None, 1, 0
 
     @property
@@ -104,17 +138,30 @@ class AutoencoderKLWan(nn.Module):
     def device(self):
         return self.model.conv2.weight.device
 
+    @staticmethod
+    def _is_enc_key(k):
+        return k.startswith("model.encoder.") or k.startswith("model.conv1.")
+
     def load_state_dict(self, state_dict, strict=True, assign=False):
-        self._prep = None
+        """Reference key names. A decode-only state dict (no `model.encoder.*` / `model.conv1.*`) is accepted even
+        with strict=True; `encode` then raises instead of running on uninitialised weights."""
+        self._prep = self._prep_enc = None
         own = set(self.state_dict().keys())
         kept = {k: v for k, v in state_dict.items() if k in own}
-        extra = [k for k in state_dict if k not in own and not (k.startswith("model.encoder.") or k.startswith("model.conv1."))]
+        extra = [k for k in state_dict if k not in own]
         if strict and extra:
             raise RuntimeError(f"unexpected keys: {extra[:5]}")
-        return super().load_state_dict(kept, strict=strict, assign=assign)
+        has_enc = any(self._is_enc_key(k) for k in kept)
+        if not has_enc:
+            for k, v in self.state_dict().items():
+                if self._is_enc_key(k):
+                    kept[k] = v
+        res = super().load_state_dict(kept, strict=strict, assign=assign)
+        self._has_encoder = has_enc
+        return res
 
     def _apply(self, fn, *a, **k):
-        self._prep = None
+        self._prep = self._prep_enc = None
         return super()._apply(fn, *a, **k)
 
     @classmethod
@@ -132,9 +179,149 @@ class AutoencoderKLWan(nn.Module):
         print(f"### missing keys: {len(m)}; \n### unexpected keys: {len(u)};")
         return model
 
+    # ------------------------------------------------------------------ encode
+    def _prepare_encoder(self):
+        if self._prep_enc is not None:
+            return self._prep_enc
+        if not self._has_encoder:
+            raise RuntimeError("AutoencoderKLWan (B200): no encoder weights were loaded (decode-only state dict); "
+                               "load a state dict with model.encoder.* / model.conv1.* before calling encode")
+        sd = {k: v for k, v in self.state_dict().items()}
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("AutoencoderKLWan (B200): parameters must live on a CUDA device; there is no CPU fallback")
+        P = "model.encoder."
+        conv = lambda n, **kw: _Conv(sd[n + ".weight"], sd[n + ".bias"], dev, **kw)  # noqa: E731
+        f32 = lambda n: sd[n].to(dev, torch.float32).reshape(-1).contiguous()  # noqa: E731
+        bf = lambda t: t.to(dev, torch.bfloat16).contiguous()  # noqa: E731
+
+        def res(pre, cin, cout):
+            d = dict(g0=f32(pre + "residual.0.gamma"), c0=conv(pre + "residual.2"), g1=f32(pre + "residual.3.gamma"),
+                     c1=conv(pre + "residual.6"), cin=cin, cout=cout)
+            if cin != cout:
+                d["w_sc"] = bf(sd[pre + "shortcut.weight"].reshape(cout, cin))
+                d["b_sc"] = bf(sd[pre + "shortcut.bias"])
+            return d
+
+        def down_conv(n):
+            """3x3 stride-2 Conv2d behind ZeroPad2d(0,1,0,1) (:96-98) as a 2x2-tap conv over the space-to-depth input:
+            input row 2y + ky = 2(y + ky//2) + ky%2, so tap (ty, tx) x sub-position (dy, dx) holds W[2ty+dy, 2tx+dx]."""
+            w = sd[n + ".weight"].to(torch.float32)
+            cout, c = w.shape[:2]
+            w2 = torch.zeros(cout, 4 * c, 1, 2, 2)
+            for ky in range(3):
+                for kx in range(3):
+                    d = (ky % 2) * 2 + (kx % 2)
+                    w2[:, d * c:(d + 1) * c, 0, ky // 2, kx // 2] = w[:, :, ky, kx]
+            return _Conv(w2, sd[n + ".bias"], dev, pad=(0, 0))
+
+        downs = []
+        for i, m in enumerate(self.enc_mods):
+            q = f"{P}downsamples.{i}."
+            if m[0] == "res":
+                downs.append(("res", res(q, m[1], m[2])))
+            else:
+                d = dict(c=m[1], conv=down_conv(q + "resample.1"))
+                if m[0] == "down3d":                         # (3,1,1) stride (2,1,1), one cached frame in front (:153-160)
+                    d["tconv"] = conv(q + "time_conv", lead=1, stride_t=2)
+                downs.append((m[0], d))
+        c = self.enc_dims[-1]
+        wqkv, bqkv = sd[P + "middle.1.to_qkv.weight"].reshape(3 * c, c), sd[P + "middle.1.to_qkv.bias"]
+        attn = dict(g=f32(P + "middle.1.norm.gamma"), w_qk=bf(wqkv[:2 * c]), b_qk=bf(bqkv[:2 * c]), w_v=bf(wqkv[2 * c:]),
+                    b_v=bf(bqkv[2 * c:]), w_o=bf(sd[P + "middle.1.proj.weight"].reshape(c, c)), b_o=bf(sd[P + "middle.1.proj.bias"]))
+        z2 = 2 * self.config.latent_channels
+        self._prep_enc = dict(conv1=conv(P + "conv1"), downs=downs, mid0=res(P + "middle.0.", c, c), attn=attn,
+                              mid2=res(P + "middle.2.", c, c), head_g=f32(P + "head.0.gamma"), head=conv(P + "head.2"),
+                              wc=sd["model.conv1.weight"].to(dev, torch.float32).reshape(z2, z2).contiguous(),
+                              bc=sd["model.conv1.bias"].to(dev, torch.float32).contiguous(),
+                              mean=self.mean.to(dev), std=self.std.to(dev))
+        return self._prep_enc
+
+    def _alloc_encoder(self, H, W, dev):
+        """Ring buffers sized for a steady-state chunk: 4 frames until the first temporal downsample, then 2, then 1."""
+        p = self._prepare_encoder()
+        tc = 4
+        p["conv1"].alloc(tc, H, W, dev)
+        for kind, d in p["downs"]:
+            if kind == "res":
+                d["c0"].alloc(tc, H, W, dev), d["c1"].alloc(tc, H, W, dev)
+            else:
+                H, W = H // 2, W // 2
+                d["conv"].alloc(tc, H, W, dev)
+                if kind == "down3d":
+                    d["tconv"].alloc(tc, H, W, dev)
+                    tc //= 2
+        for d in (p["mid0"], p["mid2"]):
+            d["c0"].alloc(tc, H, W, dev), d["c1"].alloc(tc, H, W, dev)
+        p["head"].alloc(tc, H, W, dev)
+
+    def _encode_chunk(self, a, chunk, h_out):
+        """Encoder3d.forward (:324-369) on one chunk a [tc, H, W, 32] bf16 (video frames, channels zero-padded);
+        writes the head's fp32 output [tc', H/8, W/8, 2*z] into h_out."""
+        p = self._prepare_encoder()
+        dev, bf = a.device, torch.bfloat16
+        tc, H, W, _ = a.shape
+        p["conv1"].slot(tc).copy_(a)
+        a = p["conv1"].run(tc, torch.empty(tc, H, W, self.enc_dims[0], device=dev, dtype=bf))
+        for kind, d in p["downs"]:
+            if kind == "res":
+                a = self._res_block(d, a, tc)
+                continue
+            C = d["c"]
+            if H % 2 or W % 2:
+                raise ValueError(f"AutoencoderKLWan.encode: feature map {H}x{W} is not even; H and W must be multiples of 8")
+            H, W = H // 2, W // 2
+            ops.vae_space_to_depth(a, d["conv"].slot(tc))
+            if kind == "down2d":
+                a = d["conv"].run(tc, torch.empty(tc, H, W, C, device=dev, dtype=bf))
+            elif chunk == 0:                                 # first chunk: the frame only seeds the time_conv cache (:148-151)
+                a = d["conv"].run(tc, torch.empty(tc, H, W, C, device=dev, dtype=bf))
+                d["tconv"].buf[0].copy_(a[tc - 1])
+            else:
+                d["conv"].run(tc, d["tconv"].slot(tc))
+                a = d["tconv"].run(tc, torch.empty(tc // 2, H, W, C, device=dev, dtype=bf), keep_cache=False)
+                d["tconv"].buf[0].copy_(d["tconv"].buf[tc])  # cache = last frame of this chunk (:154)
+                tc //= 2
+        a = self._res_block(p["mid0"], a, tc)
+        a = self._attention(p["attn"], a)
+        a = self._res_block(p["mid2"], a, tc)
+        ops.vae_rmsnorm_silu(a, p["head_g"], p["head"].slot(tc))
+        p["head"].run(tc, h_out, out_mode=3)
+        return tc
+
+    @torch.no_grad()
+    def _encode_one(self, x, out):
+        """x [3, T, H, W] fp32 -> out [2z, 1 + (T-1)//4, H/8, W/8] fp32: AutoencoderKLWan_.encode (:519-547)."""
+        p = self._prepare_encoder()
+        dev = x.device
+        _, T, H, W = x.shape
+        if H % 8 or W % 8:
+            raise ValueError(f"AutoencoderKLWan.encode: H and W must be multiples of 8, got {H}x{W}")
+        self._alloc_encoder(H, W, dev)
+        n_chunks = 1 + (T - 1) // 4
+        z2 = out.shape[0]
+        h_all = torch.empty(n_chunks, H // 8, W // 8, z2, device=dev, dtype=torch.float32)
+        for i in range(n_chunks):
+            frames = x[:, :1] if i == 0 else x[:, 1 + 4 * (i - 1):1 + 4 * i]
+            a = ops.vae_video_in(frames.contiguous(), 32)
+            tcl = self._encode_chunk(a, i, h_all[i:i + 1])
+            assert tcl == 1
+        ops.vae_latent_out(h_all, p["wc"], p["bc"], p["mean"], p["std"], out)
+
+    @torch.no_grad()
     def encode(self, x, return_dict=True):
-        raise NotImplementedError("AutoencoderKLWan (B200): encode is outside the accelerated hot path (SURVEY.md §8f); "
-                                  "use the reference VAE for the one conditioning encode or pass latents directly")
+        """wan_vae.py:649-664. x [B, 3, T, H, W] in [-1, 1]; frames beyond 1 + 4k are dropped like the reference does."""
+        dev = self.device
+        x = x.to(dev, torch.float32)
+        B, _, T, H, W = x.shape
+        z2 = 2 * self.config.latent_channels
+        h = torch.empty(B, z2, 1 + (T - 1) // 4, H // 8, W // 8, device=dev, dtype=torch.float32)
+        for b in range(B):
+            self._encode_one(x[b], h[b])
+        posterior = DiagonalGaussianDistribution(h)
+        if not return_dict:
+            return (posterior,)
+        return AutoencoderKLOutput(latent_dist=posterior)
 
     # ------------------------------------------------------------------ one-time operand preparation
     def _prepare(self):

@@ -134,3 +134,28 @@ def test_vae_decode_single_frame_batch(vae_gold):
         out = V.vae_decode(sd, synth.det_normal("vae_z1", (2, 16, 1, 4, 6)))
     assert out.shape == (2, 3, 1, 32, 48)
     assert rel(out, vae_gold["z1_out"]) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- Wan VAE encode
+@pytest.fixture(scope="module")
+def vae_enc_gold(golden_dir):
+    return np.load(golden_dir / "vae_enc_tiny.npz")
+
+
+@pytest.mark.parametrize("name,shape,lat", [("x9", (1, 3, 9, 32, 48), (1, 16, 3, 4, 6)),       # chunks 1, 4, 4
+                                            ("x1", (2, 3, 1, 16, 32), (2, 16, 1, 2, 4)),       # first-chunk path only, batch 2
+                                            ("x6", (1, 3, 6, 16, 16), (1, 16, 2, 2, 2))])      # trailing frame dropped
+def test_vae_encode_vs_reference(vae_enc_gold, name, shape, lat):
+    from oracle import vae as V
+    sd = synth.vae_state_dict(encoder=True)
+    with torch.no_grad():
+        out = V.vae_encode(sd, synth.det_normal("vae_" + name, shape).clamp_(-1, 1))
+    assert out.shape == (lat[0], 32, *lat[2:])
+    assert rel(out[:, :16], vae_enc_gold[name + "_mode"]) < 1e-5
+    if name == "x9":
+        assert rel(out, vae_enc_gold["x9_params"]) < 1e-5
+
+
+def test_vae_state_dict_decoder_values_do_not_depend_on_encoder_flag():
+    a, b = synth.vae_state_dict(), synth.vae_state_dict(encoder=True)
+    assert set(a) < set(b) and all(torch.equal(a[k], b[k]) for k in a)

@@ -1,4 +1,4 @@
-"""GPU parity (-m gpu) of the Wan VAE decode: CUDA path (bf16 tensor-core implicit-GEMM convs, channels-last) against
+"""GPU parity (-m gpu) of the Wan VAE decode and encode: CUDA path (bf16 tensor-core implicit-GEMM convs, channels-last) against
 the fp32 CPU oracle and the golden fixtures of the real reference. Bars: rel-L2 <= 2e-2 (bf16 mode) and PSNR >= 35 dB
 on the decoded frames (BASELINE.json), frames in [-1, 1] so peak-to-peak = 2."""
 import math
@@ -116,3 +116,55 @@ def test_pipeline_parallel_decode_equals_single_gpu(world):
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(world))
     assert all(res.values()), res
+
+
+# ---------------------------------------------------------------------------------------------- encode
+@pytest.fixture(scope="module")
+def vae_enc():
+    from stableavatar_b200.wan_vae import AutoencoderKLWan
+    m = AutoencoderKLWan()
+    m.load_state_dict(synth.vae_state_dict(encoder=True), strict=True)
+    return m.to("cuda")
+
+
+@pytest.fixture(scope="module")
+def enc_gold(golden_dir):
+    return np.load(golden_dir / "vae_enc_tiny.npz")
+
+
+@pytest.mark.parametrize("name,shape", [("x9", (1, 3, 9, 32, 48)), ("x1", (2, 3, 1, 16, 32)), ("x6", (1, 3, 6, 16, 16))])
+def test_encode_vs_golden(vae_enc, enc_gold, name, shape):
+    """Chunks 1, 4, 4 (both stride-2 time convs with their one-frame caches), the first-chunk-only path with batch 2,
+    and a clip whose trailing frame the 1 + 4k chunking drops — against the real reference's outputs."""
+    x = synth.det_normal("vae_" + name, shape).clamp_(-1, 1)
+    post = vae_enc.encode(x.cuda())[0]                      # the reference call pattern: vae.encode(x)[0].mode()
+    mode = post.mode()
+    torch.cuda.synchronize()
+    ref = enc_gold[name + "_mode"]
+    assert tuple(mode.shape) == ref.shape and mode.dtype == torch.float32
+    assert rel(mode, ref) < 2e-2
+    if name == "x9":
+        assert rel(post.parameters, enc_gold["x9_params"]) < 2e-2
+        assert torch.equal(vae_enc.encode(x.cuda()).latent_dist.mode(), mode)      # caches reset between calls
+
+
+def test_encode_ragged_tiles_vs_oracle(vae_enc):
+    """H/8, W/8 not multiples of the conv tile at any stage; 13 frames = chunks 1, 4, 4, 4."""
+    from oracle import vae as V
+    x = synth.det_normal("vae_x13", (1, 3, 13, 40, 56)).clamp_(-1, 1)
+    out = vae_enc.encode(x.cuda(), return_dict=False)[0].parameters
+    with torch.no_grad():
+        ref = V.vae_encode(synth.vae_state_dict(encoder=True), x)
+    assert out.shape == ref.shape == (1, 32, 4, 5, 7)
+    assert rel(out, ref) < 2e-2
+
+
+def test_encode_then_decode_shapes_and_decode_only_state_dict(vae_enc, vae):
+    x = synth.det_normal("vae_x5", (1, 3, 5, 32, 32)).clamp_(-1, 1)
+    z = vae_enc.encode(x.cuda()).latent_dist.mode()
+    assert z.shape == (1, 16, 2, 4, 4)
+    assert vae_enc.decode(z).sample.shape == (1, 3, 5, 32, 32)
+    with pytest.raises(RuntimeError, match="encoder weights"):
+        vae.encode(x.cuda())                                 # `vae` was loaded from a decode-only state dict
+    with pytest.raises(ValueError, match="multiples of 8"):
+        vae_enc.encode(torch.zeros(1, 3, 1, 20, 32, device="cuda"))

@@ -37,6 +37,33 @@ def gen_vae():
     print("wrote vae_tiny.npz", {k: v.shape for k, v in res.items()})
 
 
+def gen_vae_encode():
+    """Encode fixture: the REAL AutoencoderKLWan.encode on a 9-frame clip (chunks 1, 4, 4 -> 3 latent frames), on a
+    single frame (first-chunk path only), and on a 6-frame clip (one trailing frame dropped by the 1+4k chunking)."""
+    _, _, vae = import_reference()
+    m = vae.AutoencoderKLWan().eval()
+    ref_sd = m.state_dict()
+    sd = synth.vae_state_dict(encoder=True)
+    enc_keys = {k: tuple(v.shape) for k, v in ref_sd.items() if k.startswith("model.encoder.") or k.startswith("model.conv1.")}
+    mine = {k: tuple(v) for k, v in synth.vae_encoder_param_shapes().items()}
+    assert enc_keys == mine, (set(enc_keys) ^ set(mine), [(k, enc_keys[k], mine[k]) for k in enc_keys if k in mine and enc_keys[k] != mine[k]])
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    res = {}
+    with torch.no_grad():
+        x9 = synth.det_normal("vae_x9", (1, 3, 9, 32, 48)).clamp_(-1, 1)
+        d = m.encode(x9).latent_dist
+        res["x9_params"] = torch.cat([d.mean, d.logvar], 1).numpy()
+        res["x9_mode"] = d.mode().numpy()
+        x1 = synth.det_normal("vae_x1", (2, 3, 1, 16, 32)).clamp_(-1, 1)
+        res["x1_mode"] = m.encode(x1).latent_dist.mode().numpy()
+        x6 = synth.det_normal("vae_x6", (1, 3, 6, 16, 16)).clamp_(-1, 1)
+        res["x6_mode"] = m.encode(x6).latent_dist.mode().numpy()
+    np.savez_compressed(ROOT / "tests" / "golden" / "vae_enc_tiny.npz", **res)
+    print("wrote vae_enc_tiny.npz", {k: v.shape for k, v in res.items()})
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
-    gen_vae()
+    if "--encode-only" not in sys.argv:
+        gen_vae()
+    gen_vae_encode()

@@ -26,3 +26,22 @@ flop = (4.29 + (T - 1) * 13.49 + T * 0.06) * 1e12 * (h * w) / (60 * 104)
 print(f"vae decode T={T} {h}x{w}: {ms:.1f} ms (wall {1e3 * (time.perf_counter() - t0):.1f} ms), {flop / ms / 1e9:.1f} TFLOP/s, "
       f"{_lib.launch_count} kernel launches, out {tuple(out.shape)} finite={bool(torch.isfinite(out).all())} "
       f"mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+
+if "--encode" in sys.argv:
+    # Encode of the conditioning clip: x [1,3,1+4(T-1),8h,8w] -> latent [1,16,T,h,w]; 162.5 TFLOP at
+    # the full size (81 x 480 x 832).
+    vae.load_state_dict(synth.vae_state_dict(encoder=True), strict=True)
+    F = 1 + 4 * (T - 1)
+    x = out.clamp(-1, 1) if out.shape[2] == F else torch.zeros(1, 3, F, 8 * h, 8 * w, device="cuda")
+    del out
+    lat = vae.encode(x).latent_dist.mode()
+    torch.cuda.synchronize()
+    _lib.launch_count = 0
+    e0.record()
+    lat = vae.encode(x).latent_dist.mode()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    flop = 162.5e12 * (F / 81) * (h * w) / (60 * 104)
+    print(f"vae encode F={F} {8 * h}x{8 * w}: {ms:.1f} ms, {flop / ms / 1e9:.1f} TFLOP/s, {_lib.launch_count} kernel launches, "
+          f"latent {tuple(lat.shape)} finite={bool(torch.isfinite(lat).all())} mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
