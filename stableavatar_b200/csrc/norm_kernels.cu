@@ -18,7 +18,7 @@ namespace sa {
 namespace norm {
 
 constexpr int WARPS_PER_BLOCK = 8;
-constexpr int MAX_CHUNKS = 8;  // C <= 8 * 256 = 2048 per warp-row
+constexpr int MAX_CHUNKS = 20;  // C <= 20 * 256 = 5120 per warp-row (the 14B width)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -110,7 +110,7 @@ __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&v)[8]
 }
 
 template <int NCH, bool XBF, bool OBF, bool WBF>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, XBF ? 4 : 2) layernorm_kernel(const LnParams p) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 8 ? (XBF ? 4 : 2) : (XBF ? 2 : 1)) layernorm_kernel(const LnParams p) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -224,7 +224,7 @@ struct RmsParams {
 };
 
 template <int NCH>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) rmsnorm_rope_kernel(const RmsParams p) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 8 ? 4 : 2) rmsnorm_rope_kernel(const RmsParams p) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -324,7 +324,8 @@ extern "C" int sa_layernorm_modulate(const sa_ln_args* a, sa_stream_t stream_) {
   const int nch = (a->C / 8 + 31) / 32;
   if (nch <= 2) launch_ln<2>(p, grid, stream);
   else if (nch <= 6) launch_ln<6>(p, grid, stream);
-  else launch_ln<8>(p, grid, stream);
+  else if (nch <= 8) launch_ln<8>(p, grid, stream);
+  else launch_ln<20>(p, grid, stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "layernorm_kernel launch");
   return SA_OK;
@@ -358,7 +359,8 @@ extern "C" int sa_rmsnorm_rope(const sa_rms_args* a, sa_stream_t stream_) {
   const int nch = (a->C / 8 + 31) / 32;
   if (nch <= 2) rmsnorm_rope_kernel<2><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
   else if (nch <= 6) rmsnorm_rope_kernel<6><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
-  else rmsnorm_rope_kernel<8><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  else if (nch <= 8) rmsnorm_rope_kernel<8><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  else rmsnorm_rope_kernel<20><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "rmsnorm_rope_kernel launch");
   return SA_OK;

@@ -110,7 +110,9 @@ def test_full_size_gemm_linearity(ops):
     assert rel(y12[rows, 8960:], want) < 4e-3
 
 
-def test_layernorm_modulate_and_rmsnorm_rope_vs_torch(ops):
+@pytest.mark.parametrize("C", [1536, 2048, 5120])        # 1.3B width, the widest 8-chunk row, the 14B width (20 chunks)
+def test_layernorm_modulate_and_rmsnorm_rope_vs_torch(ops, C):
+    H = C // 128
     from oracle import dit as O
     g = torch.Generator(device="cuda").manual_seed(2)
     B, F, Hh, W = 2, 3, 5, 7
