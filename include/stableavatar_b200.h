@@ -78,8 +78,9 @@ int sa_flash_attn_d128(const sa_attn_args* args, sa_stream_t stream);
 
 /* Same contract for a handful of queries per (batch, head) and any head_dim % 8 == 0: the audio adapter's
  * cross-attention, 15 audio tokens x 1560 video tokens x 8 heads of 192
- * (wan/models/vocal_projector_fantasy_1B.py:259-277; SDPA branch :178-203). q_len <= 16,
- * q_len * (head_dim + kv_len) * 4 <= 200 KB. accumulate must be 0. */
+ * (wan/models/vocal_projector_fantasy_1B.py:259-277; SDPA branch :178-203), and 8 heads of 640 for the 14B adapter
+ * (vocal_projector_fantasy_14B.py). q_len <= 16, head_dim <= 768, any kv_len (keys are tiled through shared memory
+ * with a running softmax). accumulate must be 0. */
 int sa_attn_small_q(const sa_attn_args* args, int32_t head_dim, sa_stream_t stream);
 
 /* ---- LayerNorm (+affine) (+AdaLN modulation) (+gated self-residual) ------------------------------------------

@@ -136,9 +136,17 @@ def vocal_block(sd, pre, x, e0, latents, G, num_heads=8):
 
 
 def vocal_projector(sd, vocal_embeddings, video_sample_n_frames, latents, e0, e, pre="vocal_projector."):
-    """vp1B:433-450 — returns ([B, G, A, C], lens [G])."""
-    feat = linear(vocal_embeddings, sd, pre + "proj_model.proj")
-    feat = F.layer_norm(feat, (feat.shape[-1],), sd[pre + "proj_model.norm.weight"], sd[pre + "proj_model.norm.bias"], 1e-5)
+    """vp1B:433-450 — returns ([B, G, A, C], lens [G]). A state dict with proj_model.proj_1 is the 14B adapter
+    (vp14B:384-399: two Linear+LayerNorm stages 768 -> 2048 -> dim; blocks and head identical, vp14B:431-449)."""
+    if pre + "proj_model.proj_1.weight" in sd:
+        feat = vocal_embeddings
+        for n in ("1", "2"):
+            feat = linear(feat, sd, f"{pre}proj_model.proj_{n}")
+            feat = F.layer_norm(feat, (feat.shape[-1],), sd[f"{pre}proj_model.norm_{n}.weight"],
+                                sd[f"{pre}proj_model.norm_{n}.bias"], 1e-5)
+    else:
+        feat = linear(vocal_embeddings, sd, pre + "proj_model.proj")
+        feat = F.layer_norm(feat, (feat.shape[-1],), sd[pre + "proj_model.norm.weight"], sd[pre + "proj_model.norm.bias"], 1e-5)
     ranges = split_audio_sequence(feat.size(1), num_frames=video_sample_n_frames)
     x, lens = split_tensor_with_padding(feat, ranges, expand_length=4)
     G = x.size(1)
@@ -258,7 +266,10 @@ def dit_forward(sd, cfg, x, t, context, seq_len, clip_fea, y, vocal_embeddings, 
     c = F.layer_norm(c, (dim,), sd["img_emb.proj.4.weight"], sd["img_emb.proj.4.bias"], 1e-5)
     ctx = torch.cat([c, ctx], dim=1)
 
-    if vocal_embeddings.size(0) > 1:                      # 1B:1004-1007 — adapter once, replicated [0, vc, vc]
+    if cfg.get("variant") == "14B":                       # 14B:1008 — adapter on every sample, always 81 frames / 21 groups
+        video_sample_n_frames = 81
+        vc, _ = vocal_projector(sd, vocal_embeddings, 81, h, e0, e)
+    elif vocal_embeddings.size(0) > 1:                    # 1B:1004-1007 — adapter once, replicated [0, vc, vc]
         vc, _ = vocal_projector(sd, vocal_embeddings[-1:], video_sample_n_frames, h[-1:], e0[-1:], e[-1:])
         vc = torch.cat([torch.zeros_like(vc), vc, vc])
     else:

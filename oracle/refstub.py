@@ -112,3 +112,17 @@ def import_reference():
     vp.FLASH_ATTN_2_AVAILABLE = False
     vp.FLASH_ATTN_3_AVAILABLE = False
     return dit, vp, vae
+
+
+def import_reference_14b():
+    """The train_14B model module (wan/models/wan_fantasy_transformer3d_14B.py) with SDPA forced in its adapter."""
+    install_stubs()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import wan.models.wan_fantasy_transformer3d_14B as dit14
+    import wan.models.vocal_projector_fantasy_14B as vp14
+    vp14.FLASH_ATTN_2_AVAILABLE = False
+    vp14.FLASH_ATTN_3_AVAILABLE = False
+    dit14.FLASH_ATTN_2_AVAILABLE = False
+    dit14.FLASH_ATTN_3_AVAILABLE = False
+    return dit14, vp14

@@ -2,8 +2,9 @@
 // 15 audio tokens of one latent frame attend to that frame's 1560 video tokens with 8 heads of 192
 // (wan/models/vocal_projector_fantasy_1B.py:259-277, SDPA branch :178-203). 3 GFLOP per denoise step in total, so this is
 // a CUDA-core kernel bounded by the single HBM pass over K and V: one CTA per (batch, head); scores for all queries
-// live in shared memory (q_len x kv_len fp32); K rows are read once (one thread per key), V rows once (one thread per
-// output column, coalesced across the head dim).
+// live in shared memory (q_len x key-tile fp32); K rows are read once (one thread per key), V rows once (one thread per
+// output column, coalesced across the head dim). The 14B adapter (vocal_projector_fantasy_14B.py, 8 heads of 640,
+// 3600 keys per frame at 720x1280) walks the keys in tiles with a running softmax.
 #include "../../include/stableavatar_b200.h"
 #include "sa_host.h"
 #include "sa_ptx.cuh"
@@ -13,93 +14,129 @@ namespace attn_small {
 
 constexpr int MAXQ = 16;
 constexpr int THREADS = 256;
+constexpr int MAXCPT = 3;  // output columns per thread: head_dim <= 768 (192 for the 1.3B adapter, 640 for the 14B one)
 
 struct Params {
   const __nv_bfloat16* q; const __nv_bfloat16* k; const __nv_bfloat16* v; __nv_bfloat16* out;
   long long q_bs, q_ls, k_bs, k_ls, v_bs, v_ls, o_bs, o_ls;
-  int heads, q_len, kv_len, d;
+  int heads, q_len, kv_len, d, tk;  // tk: keys per tile (scores of one tile live in shared memory)
   float scale;
 };
 
+// Keys are walked in tiles of `tk` with the usual running (max, sum) rescale, so kv_len is unbounded; when the whole
+// row of scores fits (the 1.3B shapes) there is a single tile and the rescale factors are all 1.
 __global__ void __launch_bounds__(THREADS) attn_small_kernel(const Params p) {
   extern __shared__ float smem[];
   float* sq = smem;                      // [q_len][d]
-  float* ss = smem + p.q_len * p.d;      // [q_len][kv_len]
+  float* ss = sq + p.q_len * p.d;        // [q_len][tk]
+  float* s_m = ss + p.q_len * p.tk;      // [MAXQ] running max
+  float* s_l = s_m + MAXQ;               // [MAXQ] running sum
+  float* s_f = s_l + MAXQ;               // [MAXQ] rescale factor of the current tile
   const int h = blockIdx.x % p.heads, b = blockIdx.x / p.heads;
   const __nv_bfloat16* qb = p.q + (long long)b * p.q_bs + h * p.d;
   const __nv_bfloat16* kb = p.k + (long long)b * p.k_bs + h * p.d;
   const __nv_bfloat16* vb = p.v + (long long)b * p.v_bs + h * p.d;
   for (int i = threadIdx.x; i < p.q_len * p.d; i += THREADS)
     sq[i] = __bfloat162float(qb[(long long)(i / p.d) * p.q_ls + (i % p.d)]) * p.scale;
+  if (threadIdx.x < MAXQ) {
+    s_m[threadIdx.x] = -INFINITY;
+    s_l[threadIdx.x] = 0.f;
+  }
+  float acc[MAXCPT][MAXQ];
+#pragma unroll
+  for (int cc = 0; cc < MAXCPT; ++cc)
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) acc[cc][i] = 0.f;
   __syncthreads();
 
-  // S = (q * scale) K^T : one thread per key
-  for (int j = threadIdx.x; j < p.kv_len; j += THREADS) {
-    float acc[MAXQ];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t0 = 0; t0 < p.kv_len; t0 += p.tk) {
+    const int tn = min(p.tk, p.kv_len - t0);
+    // S = (q * scale) K^T : one thread per key
+    for (int j = threadIdx.x; j < tn; j += THREADS) {
+      float sc[MAXQ];
 #pragma unroll
-    for (int i = 0; i < MAXQ; ++i) acc[i] = 0.f;
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + (long long)j * p.k_ls);
-    for (int c = 0; c < p.d / 8; ++c) {
-      const uint4 u = kr[c];
-      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
-      float kv[8];
+      for (int i = 0; i < MAXQ; ++i) sc[i] = 0.f;
+      const uint4* kr = reinterpret_cast<const uint4*>(kb + (long long)(t0 + j) * p.k_ls);
+      for (int c = 0; c < p.d / 8; ++c) {
+        const uint4 u = kr[c];
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+        float kv[8];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __bfloat1622float2(hh[t]);
-        kv[2 * t] = f.x;
-        kv[2 * t + 1] = f.y;
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __bfloat1622float2(hh[t]);
+          kv[2 * t] = f.x;
+          kv[2 * t + 1] = f.y;
+        }
+#pragma unroll
+        for (int i = 0; i < MAXQ; ++i) {
+          if (i < p.q_len) {
+            const float* qr = sq + i * p.d + c * 8;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) sc[i] = fmaf(qr[t], kv[t], sc[i]);
+          }
+        }
       }
 #pragma unroll
-      for (int i = 0; i < MAXQ; ++i) {
-        if (i < p.q_len) {
-          const float* qr = sq + i * p.d + c * 8;
+      for (int i = 0; i < MAXQ; ++i)
+        if (i < p.q_len) ss[i * p.tk + j] = sc[i];
+    }
+    __syncthreads();
+
+    // running softmax per query row: one warp per row
+    for (int i = warp; i < p.q_len; i += THREADS / 32) {
+      float* row = ss + i * p.tk;
+      float mx = -INFINITY;
+      for (int j = lane; j < tn; j += 32) mx = fmaxf(mx, row[j]);
 #pragma unroll
-          for (int t = 0; t < 8; ++t) acc[i] = fmaf(qr[t], kv[t], acc[i]);
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float m_old = s_m[i];
+      const float m_new = fmaxf(m_old, mx);
+      float sum = 0.f;
+      for (int j = lane; j < tn; j += 32) {
+        const float e = __expf(row[j] - m_new);
+        row[j] = e;
+        sum += e;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) {
+        const float f = __expf(m_old - m_new);  // 0 on the first tile (m_old = -inf)
+        s_f[i] = f;
+        s_l[i] = s_l[i] * f + sum;
+        s_m[i] = m_new;
+      }
+    }
+    __syncthreads();
+
+    // O = O * f + P V : one thread per output column (up to MAXCPT columns per thread), V rows read coalesced
+#pragma unroll
+    for (int cc = 0; cc < MAXCPT; ++cc) {
+      const int c = threadIdx.x + cc * THREADS;
+      if (c < p.d) {
+#pragma unroll
+        for (int i = 0; i < MAXQ; ++i)
+          if (i < p.q_len) acc[cc][i] *= s_f[i];
+        for (int j = 0; j < tn; ++j) {
+          const float vv = __bfloat162float(vb[(long long)(t0 + j) * p.v_ls + c]);
+#pragma unroll
+          for (int i = 0; i < MAXQ; ++i)
+            if (i < p.q_len) acc[cc][i] = fmaf(ss[i * p.tk + j], vv, acc[cc][i]);
         }
       }
     }
-#pragma unroll
-    for (int i = 0; i < MAXQ; ++i)
-      if (i < p.q_len) ss[i * p.kv_len + j] = acc[i];
+    __syncthreads();
   }
-  __syncthreads();
 
-  // softmax per query row: one warp per row
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = warp; i < p.q_len; i += THREADS / 32) {
-    float* row = ss + i * p.kv_len;
-    float mx = -INFINITY;
-    for (int j = lane; j < p.kv_len; j += 32) mx = fmaxf(mx, row[j]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int j = lane; j < p.kv_len; j += 32) {
-      const float e = __expf(row[j] - mx);
-      row[j] = e;
-      sum += e;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.0f / sum;
-    for (int j = lane; j < p.kv_len; j += 32) row[j] *= inv;
-  }
-  __syncthreads();
-
-  // O = P V : one thread per output column
-  for (int c = threadIdx.x; c < p.d; c += THREADS) {
-    float acc[MAXQ];
-#pragma unroll
-    for (int i = 0; i < MAXQ; ++i) acc[i] = 0.f;
-    for (int j = 0; j < p.kv_len; ++j) {
-      const float vv = __bfloat162float(vb[(long long)j * p.v_ls + c]);
+  for (int cc = 0; cc < MAXCPT; ++cc) {
+    const int c = threadIdx.x + cc * THREADS;
+    if (c < p.d) {
+      __nv_bfloat16* ob = p.out + (long long)b * p.o_bs + h * p.d + c;
 #pragma unroll
       for (int i = 0; i < MAXQ; ++i)
-        if (i < p.q_len) acc[i] = fmaf(ss[i * p.kv_len + j], vv, acc[i]);
+        if (i < p.q_len) ob[(long long)i * p.o_ls] = __float2bfloat16_rn(acc[cc][i] / s_l[i]);
     }
-    __nv_bfloat16* ob = p.out + (long long)b * p.o_bs + h * p.d + c;
-#pragma unroll
-    for (int i = 0; i < MAXQ; ++i)
-      if (i < p.q_len) ob[(long long)i * p.o_ls] = __float2bfloat16_rn(acc[i]);
   }
 }
 
@@ -116,11 +153,15 @@ extern "C" int sa_attn_small_q(const sa_attn_args* a, int32_t head_dim, sa_strea
     return SA_ERR_BAD_ARG;
   }
   if (a->k_ls % 8 || a->k_bs % 8) { set_error("sa_attn_small_q: k strides must be multiples of 8"); return SA_ERR_BAD_ARG; }
-  const size_t smem = (size_t)a->q_len * (head_dim + a->kv_len) * sizeof(float);
-  if (a->q_len > MAXQ || smem > 200 * 1024) {
-    set_error("sa_attn_small_q: unsupported shape (q_len %d > %d or %zu B of scores > 200 KB)", a->q_len, MAXQ, smem);
+  if (a->q_len > MAXQ || head_dim > MAXCPT * THREADS) {
+    set_error("sa_attn_small_q: unsupported shape (q_len %d > %d or head_dim %d > %d)", a->q_len, MAXQ, head_dim, MAXCPT * THREADS);
     return SA_ERR_UNSUPPORTED;
   }
+  // keys per tile: whatever of 200 KB the queries leave, in multiples of 32
+  const size_t fixed = ((size_t)a->q_len * head_dim + 3 * MAXQ) * sizeof(float);
+  int tk = (int)((200 * 1024 - fixed) / (a->q_len * sizeof(float))) / 32 * 32;
+  if (tk > a->kv_len) tk = a->kv_len;
+  const size_t smem = fixed + (size_t)a->q_len * tk * sizeof(float);
   if (a->accumulate) { set_error("sa_attn_small_q: accumulate not supported"); return SA_ERR_UNSUPPORTED; }
   Params p;
   p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
@@ -129,7 +170,7 @@ extern "C" int sa_attn_small_q(const sa_attn_args* a, int32_t head_dim, sa_strea
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.q_bs = a->q_bs; p.q_ls = a->q_ls; p.k_bs = a->k_bs; p.k_ls = a->k_ls;
   p.v_bs = a->v_bs; p.v_ls = a->v_ls; p.o_bs = a->o_bs; p.o_ls = a->o_ls;
-  p.heads = a->heads; p.q_len = a->q_len; p.kv_len = a->kv_len; p.d = head_dim; p.scale = a->scale;
+  p.heads = a->heads; p.q_len = a->q_len; p.kv_len = a->kv_len; p.d = head_dim; p.tk = tk; p.scale = a->scale;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -16,6 +16,10 @@ DIT_1_3B = dict(model_type="i2v", patch_size=(1, 2, 2), text_len=512, in_dim=36,
 # Small stand-in used by CPU-sized parity cases. dim/num_heads are fixed by the reference's audio adapter, which is
 # hard-wired to 1536 channels (wan/models/wan_fantasy_transformer3d_1B.py:872) and by the 128-wide RoPE split.
 DIT_TINY = dict(DIT_1_3B, ffn_dim=512, text_dim=128, text_len=24, num_layers=2)
+# train_14B architecture (wan/models/wan_fantasy_transformer3d_14B.py:735, wan/configs/wan_i2v_14B.py:26-35): the adapter
+# follows the DiT width (audio_proj_dim = dim, 8 heads) and has a two-stage audio projection 768 -> 2048 -> dim.
+DIT_14B = dict(DIT_1_3B, dim=5120, ffn_dim=13824, num_heads=40, num_layers=40, variant="14B")
+DIT_14B_TINY = dict(DIT_14B, dim=512, num_heads=4, ffn_dim=1024, text_dim=128, text_len=24, num_layers=2)
 
 
 def _rng(name: str, seed: int) -> np.random.Generator:
@@ -87,11 +91,20 @@ def dit_param_shapes(cfg: dict) -> dict:
     lin("img_emb.proj.3", 1280, d)
     s["img_emb.proj.4.weight"] = (d,)
     s["img_emb.proj.4.bias"] = (d,)
-    # audio adapter (vocal_projector_fantasy_1B.py:402-425): 768 -> 1536, 2 blocks, 8 heads, ffn 3072
-    a, v = 1536, "vocal_projector."
-    lin(v + "proj_model.proj", 768, a, bias=False)
-    s[v + "proj_model.norm.weight"] = (a,)
-    s[v + "proj_model.norm.bias"] = (a,)
+    # audio adapter (vocal_projector_fantasy_1B.py:402-425): 768 -> 1536, 2 blocks, 8 heads, ffn 3072;
+    # 14B (vocal_projector_fantasy_14B.py:384-425): 768 -> 2048 -> dim, blocks at the DiT width
+    v = "vocal_projector."
+    if cfg.get("variant") == "14B":
+        a = d
+        for n, (i, o) in (("1", (768, 2048)), ("2", (2048, a))):
+            lin(f"{v}proj_model.proj_{n}", i, o, bias=False)
+            s[f"{v}proj_model.norm_{n}.weight"] = (o,)
+            s[f"{v}proj_model.norm_{n}.bias"] = (o,)
+    else:
+        a = 1536
+        lin(v + "proj_model.proj", 768, a, bias=False)
+        s[v + "proj_model.norm.weight"] = (a,)
+        s[v + "proj_model.norm.bias"] = (a,)
     for i in range(2):
         p = f"{v}blocks.{i}."
         s[p + "modulation"] = (1, 6, a)

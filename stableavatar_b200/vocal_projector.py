@@ -1,7 +1,9 @@
 """Audio adapter ("vocal projector") of StableAvatar on the B200 C-ABI kernels.
 
-Mirrors wan/models/vocal_projector_fantasy_1B.py:402-450 (FantasyTalkingVocalCondition1BModel) and the window helpers
-of wan/models/vocal_projector_fantasy.py:39-131 — same constructor arguments, parameter names and forward signature.
+Mirrors wan/models/vocal_projector_fantasy_1B.py:402-450 (FantasyTalkingVocalCondition1BModel), its 14B sibling
+wan/models/vocal_projector_fantasy_14B.py:384-449 (FantasyTalkingVocalCondition14BModel: two-stage audio projection,
+blocks at the DiT width = 8 heads of 640) and the window helpers of wan/models/vocal_projector_fantasy.py:39-131 — same
+constructor arguments, parameter names and forward signature.
 The adapter's residual stream is fp32 (nn.LayerNorm output under autocast, default dtype=torch.float32 in
 VocalAttentionBlock.forward) while every Linear / attention runs in bf16.
 """
@@ -96,11 +98,24 @@ class VocalProjModel(nn.Module):
         self.norm = _Norm(cross_attention_dim)
 
 
+class VocalProjModel14B(nn.Module):
+    """vp14B.py:384-399: Linear(768, 2048, no bias) + LayerNorm, Linear(2048, dim, no bias) + LayerNorm."""
+
+    def __init__(self, audio_in_dim, cross_attention_dim):
+        super().__init__()
+        self.proj_1 = _Linear(audio_in_dim, 2048, bias=False)
+        self.norm_1 = _Norm(2048)
+        self.proj_2 = _Linear(2048, cross_attention_dim, bias=False)
+        self.norm_2 = _Norm(cross_attention_dim)
+
+
 class FantasyTalkingVocalCondition1BModel(nn.Module):
+    _proj_cls = VocalProjModel
+
     def __init__(self, audio_in_dim: int, audio_proj_dim: int, dit_dim: int):
         super().__init__()
         self.audio_in_dim, self.audio_proj_dim = audio_in_dim, audio_proj_dim
-        self.proj_model = VocalProjModel(audio_in_dim, audio_proj_dim)
+        self.proj_model = self._proj_cls(audio_in_dim, audio_proj_dim)
         self.blocks = nn.ModuleList([VocalAttentionBlock(audio_proj_dim, dit_dim, audio_proj_dim * 2, 8) for _ in range(2)])
         self.final_head = Final_Head(audio_proj_dim, audio_proj_dim)
         self._prep = None
@@ -117,6 +132,13 @@ class FantasyTalkingVocalCondition1BModel(nn.Module):
             self._prep = dict(blocks=blocks, mods=mods, head_mod=self.final_head.modulation.reshape(2, -1).contiguous())
         return self._prep
 
+    def _project(self, a):
+        """VocalProjModel (vp1B.py:389-399): bf16 Linear, then nn.LayerNorm whose autocast output is fp32."""
+        pm = self.proj_model
+        feat = ops.gemm(a, pm.proj.weight)
+        return ops.layernorm(feat, weight=pm.norm.weight, bias=pm.norm.bias, eps=1e-5, out_dtype=torch.float32,
+                             round_bf16=False)
+
     def _window_table(self, T, num_frames, device):
         key = (T, num_frames, str(device))
         if key not in self._tables:
@@ -131,10 +153,7 @@ class FantasyTalkingVocalCondition1BModel(nn.Module):
         p = self._prepare()
         B, T, _ = vocal_embeddings.shape
         C = self.audio_proj_dim
-        pm = self.proj_model
-        feat = ops.gemm(vocal_embeddings.reshape(B * T, -1).to(torch.bfloat16), pm.proj.weight)
-        feat = ops.layernorm(feat, weight=pm.norm.weight, bias=pm.norm.bias, eps=1e-5, out_dtype=torch.float32,
-                             round_bf16=False)
+        feat = self._project(vocal_embeddings.reshape(B * T, -1).to(torch.bfloat16))
         table, G, A, lens = self._window_table(T, video_sample_n_frames, feat.device)
         L = latents.shape[1]
         if L % G != 0:
@@ -168,3 +187,17 @@ class FantasyTalkingVocalCondition1BModel(nn.Module):
         if B > 1:
             lens = torch.cat([lens] * 3)
         return ctx, lens
+
+
+class FantasyTalkingVocalCondition14BModel(FantasyTalkingVocalCondition1BModel):
+    """vp14B.py:402-449. Same blocks / head / window logic as the 1B adapter; `audio_proj_dim` is the DiT width, so the
+    8 attention heads are 640 wide (sa_attn_small_q tiles the keys), and the audio projection has two stages."""
+    _proj_cls = VocalProjModel14B
+
+    def _project(self, a):
+        pm = self.proj_model
+        f1 = ops.gemm(a, pm.proj_1.weight)
+        f1 = ops.layernorm(f1, weight=pm.norm_1.weight, bias=pm.norm_1.bias, eps=1e-5, round_bf16=False)   # -> bf16 for proj_2
+        f2 = ops.gemm(f1, pm.proj_2.weight)
+        return ops.layernorm(f2, weight=pm.norm_2.weight, bias=pm.norm_2.bias, eps=1e-5, out_dtype=torch.float32,
+                             round_bf16=False)

@@ -20,7 +20,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .vocal_projector import FantasyTalkingVocalCondition1BModel, _Linear, _Norm, _param
+from .vocal_projector import (FantasyTalkingVocalCondition1BModel, FantasyTalkingVocalCondition14BModel, _Linear, _Norm,
+                              _param)
 
 
 def rope_params(max_seq_len, dim, theta=10000):
@@ -115,6 +116,11 @@ class _Conv3dParams(nn.Module):
 
 
 class WanTransformer3DFantasyModel(nn.Module):
+    _cfg_audio_trick = True            # 1B.py:1004-1007: adapter once on the last CFG sample, replicated as [0, vc, vc]
+
+    def _make_vocal_projector(self, dim):
+        return FantasyTalkingVocalCondition1BModel(audio_in_dim=768, audio_proj_dim=1536, dit_dim=dim)
+
     def __init__(self, model_type="t2v", patch_size=(1, 2, 2), text_len=512, in_dim=16, dim=2048, ffn_dim=8192,
                  freq_dim=256, text_dim=4096, out_dim=16, num_heads=16, num_layers=32, window_size=(-1, -1),
                  qk_norm=True, cross_attn_norm=True, eps=1e-6, in_channels=16, hidden_size=2048):
@@ -142,7 +148,7 @@ class WanTransformer3DFantasyModel(nn.Module):
             self.img_emb = MLPProj(1280, dim)
         self.teacache = None
         self.sp_world_size, self.sp_world_rank, self.sp_group = 1, 0, None
-        self.vocal_projector = FantasyTalkingVocalCondition1BModel(audio_in_dim=768, audio_proj_dim=1536, dit_dim=dim)
+        self.vocal_projector = self._make_vocal_projector(dim)
         self._prep = None
         self.hooks = None          # test instrumentation: dict collecting per-block outputs when set
 
@@ -358,7 +364,7 @@ class WanTransformer3DFantasyModel(nn.Module):
         h3 = h.view(B, L, C)
         e0_3 = e0.view(B, 6, C)
         vocal_embeddings = vocal_embeddings.to(dev)
-        if vocal_embeddings.size(0) > 1:
+        if vocal_embeddings.size(0) > 1 and self._cfg_audio_trick:
             vc, _ = self.vocal_projector(vocal_embeddings=vocal_embeddings[-1:], video_sample_n_frames=video_sample_n_frames,
                                          latents=h3[-1:], e0=e0_3[-1:], e=e_bf[-1:])
             vc = torch.cat([torch.zeros_like(vc), vc, vc])
@@ -501,3 +507,23 @@ class WanTransformer3DFantasyModel(nn.Module):
         qg = q.view(B * G, Ll // G, nh, 128)
         kg = kvv.view(B * G, -1, 2, nh, 128)
         ops.flash_attn(qg, kg[:, :, 0], kg[:, :, 1], out=a.view(B * G, Ll // G, nh, 128), accumulate=True)
+
+
+class WanTransformer3DFantasy14BModel(WanTransformer3DFantasyModel):
+    """Drop-in for `WanTransformer3DFantasy14BModel` (wan/models/wan_fantasy_transformer3d_14B.py:735, forward
+    :922-1150) — the train_14B architecture (dim 5120, 40 heads, 40 layers, ffn 13824 with wan/configs/wan_i2v_14B.py).
+    Differences from the 1.3B class, all reproduced: the adapter is FantasyTalkingVocalCondition14BModel at the DiT
+    width (:866); `forward` has no `video_sample_n_frames` — the audio is always split for 81 frames and the audio
+    cross-attention always uses 21 token groups (:569, :1008); the adapter runs on every sample of the batch (no
+    [0, vc, vc] replication)."""
+    _cfg_audio_trick = False
+
+    def _make_vocal_projector(self, dim):
+        return FantasyTalkingVocalCondition14BModel(audio_in_dim=768, audio_proj_dim=dim, dit_dim=dim)
+
+    @torch.no_grad()
+    def forward(self, x, t, context, seq_len, clip_fea=None, y=None, cond_flag=True, vocal_embeddings=None,
+                is_clip_level_modeling=False):
+        return super().forward(x, t, context, seq_len, clip_fea=clip_fea, y=y, cond_flag=cond_flag,
+                               vocal_embeddings=vocal_embeddings, is_clip_level_modeling=is_clip_level_modeling,
+                               video_sample_n_frames=81)

@@ -159,3 +159,24 @@ def test_vae_encode_vs_reference(vae_enc_gold, name, shape, lat):
 def test_vae_state_dict_decoder_values_do_not_depend_on_encoder_flag():
     a, b = synth.vae_state_dict(), synth.vae_state_dict(encoder=True)
     assert set(a) < set(b) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+# ---------------------------------------------------------------------------------------------- train_14B architecture
+@pytest.mark.parametrize("tag,kw", [("A", dict(batch=3)), ("C", dict(batch=1, seed=2))])
+def test_14b_architecture_vs_reference(golden_dir, tag, kw):
+    """WanTransformer3DFantasy14BModel at a CPU-sized width: two-stage audio projection, adapter at the DiT width run on
+    every sample of the batch (no [0, vc, vc] replication), 21 audio groups hard-coded."""
+    gold = np.load(golden_dir / "dit14b_tiny.npz")
+    cfg = synth.DIT_14B_TINY
+    sd14 = synth.dit_state_dict(cfg)
+    inp = synth.dit_inputs(cfg, frames=81, height=32, width=32, **kw)
+    hooks = {}
+    with torch.no_grad():
+        out = O.dit_forward(sd14, cfg, inp["x"], inp["t"], inp["context"], inp["seq_len"], inp["clip_fea"], inp["y"],
+                            inp["vocal_embeddings"], hooks=hooks)
+    assert rel(out, gold[tag + "_out"]) < 1e-5
+    assert rel(hooks["vocal_context"][:, :, ::4], gold[tag + "_vocal_context"]) < 1e-5
+    for i in range(2):
+        assert rel(hooks[f"block{i}"][:, :, ::4], gold[f"{tag}_block{i}"]) < 1e-5
+    if tag == "A":                                  # sample 0 gets the adapter's answer to silent audio, not zeros
+        assert hooks["vocal_context"][0].abs().max() > 0

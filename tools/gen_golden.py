@@ -113,12 +113,44 @@ def gen_dit():
     print("wrote", GOLD / "dit_tiny.npz", sum(v.nbytes for v in res.values()) / 1e6, "MB raw")
 
 
+def gen_dit_14b():
+    """train_14B architecture at a CPU-sized width (dim 512 = 4 heads of 128, adapter 8 heads of 64): the real
+    WanTransformer3DFantasy14BModel on 81 frames @ 32x32 (21 latent frames of 2x2 tokens — the class hard-codes 21)."""
+    from oracle.refstub import import_reference_14b
+    dit14, _ = import_reference_14b()
+    cfg = synth.DIT_14B_TINY
+    keys = ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim", "out_dim",
+            "num_heads", "num_layers")
+    m = dit14.WanTransformer3DFantasy14BModel(**{k: cfg[k] for k in keys}).eval()
+    m.load_state_dict(synth.dit_state_dict(cfg), strict=True)
+    res = {}
+    for tag, kw in (("A", dict(batch=3)), ("C", dict(batch=1, seed=2))):
+        inp = synth.dit_inputs(cfg, frames=81, height=32, width=32, **kw)
+        blocks = {}
+        hs = [b.register_forward_hook(lambda mod, a, out, i=i: blocks.__setitem__(f"block{i}", out.detach().clone()))
+              for i, b in enumerate(m.blocks)]
+        hs.append(m.vocal_projector.register_forward_hook(
+            lambda mod, a, out: blocks.__setitem__("vocal_context", out[0].detach().clone())))
+        with torch.no_grad():
+            out = m(x=inp["x"], t=inp["t"], context=inp["context"], seq_len=inp["seq_len"], clip_fea=inp["clip_fea"],
+                    y=inp["y"], vocal_embeddings=inp["vocal_embeddings"])
+        for h in hs:
+            h.remove()
+        res[tag + "_out"] = out.numpy()
+        for k, v in blocks.items():
+            res[f"{tag}_{k}"] = v[:, :, ::4].numpy()                       # every 4th channel
+    np.savez_compressed(GOLD / "dit14b_tiny.npz", **res)
+    print("wrote", GOLD / "dit14b_tiny.npz", {k: v.shape for k, v in res.items()})
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_grad_enabled(False)
     if what in ("dit", "all"):
         gen_dit()
+    if what in ("dit14b", "all"):
+        gen_dit_14b()
     if what in ("vae", "all"):
         from tools.gen_golden_vae import gen_vae
         gen_vae()
