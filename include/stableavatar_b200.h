@@ -207,6 +207,34 @@ int sa_vae_latent_in(const void* z, const void* wc, const void* bc, const void* 
                      int32_t Cz, int64_t P, int32_t Cpad, sa_stream_t stream);
 
 
+/* ---- sequence-parallel exchange over NVLink peer memory (replaces wan/dist/wan_xfuser.py:102-110) -----------------
+ * Ulysses all-to-all of the DiT self-attention as direct peer stores: the caller maps every rank's receive buffers
+ * (CUDA IPC) and passes the P base pointers. Head split: hg head groups x qs = P / hg query splits, rank = g * qs + s.
+ *   sa_sp_scatter_qkv: src = local q|k|v rows [B, Ll, 3, heads, 128] bf16 (row stride ld elements) ->
+ *       dst_a[r] = rank r's kv_recv [P, Ll, B, 2, heads/hg, 128] (slot = this rank) for the qs ranks of each head group,
+ *       dst_b[r] = rank r's q_recv [hg, Ll, B, heads/hg, 128] (slot = this rank / qs) for the rank with s == this rank % qs.
+ *   sa_sp_scatter_o: src = attention output [hg, Ll, B, heads/hg, 128] (source ranks i * qs + s) ->
+ *       dst_a[r] = rank r's o_recv [B, Ll, heads, 128], head columns of this rank's group.
+ *   sa_sp_barrier: sig[r] = rank r's flag array (uint32 [P], zero-initialised), epoch = local uint32 counter. Orders all
+ *       earlier stores of this stream before, and all peers' earlier stores after; traps after a bounded spin.
+ * No launch is issued on a peer's device; the kernels only store through the mapped pointers. */
+typedef struct {
+  const void* src;
+  void* dst_a[8];
+  void* dst_b[8];
+  int64_t ld;
+  int32_t B, Ll, heads, head_dim, P, rank, hg;
+} sa_sp_args;
+int sa_sp_scatter_qkv(const sa_sp_args* args, sa_stream_t stream);
+int sa_sp_scatter_o(const sa_sp_args* args, sa_stream_t stream);
+int sa_sp_barrier(void* const* sig, void* epoch, int32_t P, int32_t rank, sa_stream_t stream);
+/* CUDA IPC for the mappings above. sa_ipc_export: 64-byte handle of the cudaMalloc allocation containing ptr + the byte
+ * offset of ptr inside it. sa_ipc_open: map a PEER process's allocation; call with the device that will launch the
+ * scatter kernels current (peer access is enabled for that device); returns the allocation base. sa_ipc_close unmaps. */
+int sa_ipc_export(const void* ptr, void* handle64, int64_t* offset);
+int sa_ipc_open(const void* handle64, void** base);
+int sa_ipc_close(void* base);
+
 /* ---- Wan VAE encode helpers (wan/models/wan_vae.py:519-547) -------------------------------------------------------
  * out[t, y, x, (dy*2 + dx)*C + c] = in[t, 2y + dy, 2x + dx, c]: bf16 [T,H,W,C] -> [T,H/2,W/2,4C] (H, W even), the input
  * layout of the stride-2 Conv2d of Resample('downsample2d'/'downsample3d') (:96-104). */

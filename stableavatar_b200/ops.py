@@ -324,3 +324,60 @@ def vae_latent_out(h, wc, bc, mean, std, out):
                                       C.c_void_p(mean.data_ptr()), C.c_void_p(std.data_ptr()), C.c_void_p(out.data_ptr()),
                                       C2 // 2, C.c_int64(h.numel() // C2), L.stream_ptr()), "sa_vae_latent_out")
     return out
+
+
+# ---------------------------------------------------------------------------------------------- sequence-parallel exchange
+class SpArgs(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst_a", C.c_void_p * 8), ("dst_b", C.c_void_p * 8), ("ld", C.c_int64),
+                ("B", C.c_int32), ("Ll", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32), ("P", C.c_int32),
+                ("rank", C.c_int32), ("hg", C.c_int32)]
+
+
+def _sp_args(src, dst_a, dst_b, ld, B, Ll, heads, P, rank, hg):
+    a = SpArgs(src=src.data_ptr(), ld=ld, B=B, Ll=Ll, heads=heads, head_dim=128, P=P, rank=rank, hg=hg)
+    for r in range(P):
+        a.dst_a[r] = dst_a[r]
+        a.dst_b[r] = dst_b[r] if dst_b is not None else None
+    return a
+
+
+def sp_scatter_qkv(qkv, kv_ptrs, q_ptrs, *, B, Ll, heads, P, rank, hg):
+    """qkv: local [B*Ll, >= 3*heads*128] bf16 rows (q | k | v) -> peers' kv_recv / q_recv — sa_sp_scatter_qkv."""
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[0] == B * Ll
+    a = _sp_args(qkv, kv_ptrs, q_ptrs, qkv.stride(0), B, Ll, heads, P, rank, hg)
+    L.check(L.lib().sa_sp_scatter_qkv(C.byref(a), L.stream_ptr()), "sa_sp_scatter_qkv")
+
+
+def sp_scatter_o(o, o_ptrs, *, B, Ll, heads, P, rank, hg):
+    """o: this rank's attention output [P/qs * Ll, B, heads/hg, 128] bf16 contiguous -> peers' o_recv — sa_sp_scatter_o."""
+    _need_cuda(o)
+    assert o.dtype == torch.bfloat16 and o.is_contiguous()
+    a = _sp_args(o, o_ptrs, None, 0, B, Ll, heads, P, rank, hg)
+    L.check(L.lib().sa_sp_scatter_o(C.byref(a), L.stream_ptr()), "sa_sp_scatter_o")
+
+
+def sp_barrier(sig_ptrs, epoch, P, rank):
+    """Flag barrier across the ranks whose flag arrays are mapped at sig_ptrs — sa_sp_barrier."""
+    arr = (C.c_void_p * 8)(*([sig_ptrs[r] for r in range(P)] + [None] * (8 - P)))
+    L.check(L.lib().sa_sp_barrier(arr, C.c_void_p(epoch.data_ptr()), P, rank, L.stream_ptr()), "sa_sp_barrier")
+
+
+def ipc_export(t):
+    """(64-byte handle, byte offset) of the device allocation holding tensor t — sa_ipc_export."""
+    _need_cuda(t)
+    h = C.create_string_buffer(64)
+    off = C.c_int64(0)
+    L.check(L.lib().sa_ipc_export(C.c_void_p(t.data_ptr()), h, C.byref(off)), "sa_ipc_export")
+    return h.raw, off.value
+
+
+def ipc_open(handle):
+    """Base address of a peer process's allocation mapped for the CURRENT device — sa_ipc_open."""
+    base = C.c_void_p(0)
+    L.check(L.lib().sa_ipc_open(C.c_char_p(handle), C.byref(base)), "sa_ipc_open")
+    return base.value
+
+
+def ipc_close(base):
+    L.check(L.lib().sa_ipc_close(C.c_void_p(base)), "sa_ipc_close")

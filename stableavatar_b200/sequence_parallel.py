@@ -125,20 +125,22 @@ def exchange_qkv(pl, q, k, v, group=None, kv=None):
     P, hp, hg, qs = pl.world, pl.hp, pl.hg, pl.qs
     n_kv, n_q = Ll * B * 2 * hp * d, Ll * B * hp * d
     # K|V for head group g -> every rank of that group: [hg, Ll, B, 2, hp, d], repeated for the qs query splits
-    if kv is None:                                           # kv: optional [B, Ll, 2, nh, d] view holding k and v side by side
-        kv = torch.stack([k, v], dim=2)
-    kv = kv.reshape(B, Ll, 2, hg, hp, d).permute(3, 1, 0, 2, 4, 5)
-    kv_send = (kv.repeat_interleave(qs, dim=0) if qs > 1 else kv.contiguous()).reshape(-1)
-    kv_recv = torch.empty(P * n_kv, device=q.device, dtype=q.dtype)
-    # Q for head group g -> only the rank (g, s = my query split): [hg, Ll, B, hp, d]
-    q_send = q.view(B, Ll, hg, hp, d).permute(2, 1, 0, 3, 4).contiguous().reshape(-1)
+    with ops.timed("sp_pack"):
+        if kv is None:                                       # kv: optional [B, Ll, 2, nh, d] view holding k and v side by side
+            kv = torch.stack([k, v], dim=2)
+        kv = kv.reshape(B, Ll, 2, hg, hp, d).permute(3, 1, 0, 2, 4, 5)
+        kv_send = (kv.repeat_interleave(qs, dim=0) if qs > 1 else kv.contiguous()).reshape(-1)
+        kv_recv = torch.empty(P * n_kv, device=q.device, dtype=q.dtype)
+        # Q for head group g -> only the rank (g, s = my query split): [hg, Ll, B, hp, d]
+        q_send = q.view(B, Ll, hg, hp, d).permute(2, 1, 0, 3, 4).contiguous().reshape(-1)
     in_splits = [n_q if dst % qs == pl.s else 0 for dst in range(P)]
     out_splits = [n_q if src in pl.q_sources else 0 for src in range(P)]
     q_recv = torch.empty(len(pl.q_sources) * n_q, device=q.device, dtype=q.dtype)
 
     def exchange():
-        all_to_all_single(kv_recv, kv_send, [n_kv] * P, [n_kv] * P, group)
-        all_to_all_single(q_recv, q_send, out_splits, in_splits, group)
+        with ops.timed("sp_a2a_qkv"):
+            all_to_all_single(kv_recv, kv_send, [n_kv] * P, [n_kv] * P, group)
+            all_to_all_single(q_recv, q_send, out_splits, in_splits, group)
     comm_point(exchange)
     return q_recv.view(len(pl.q_sources) * Ll, B, hp, d), kv_recv.view(P * Ll, B, 2, hp, d)
 
@@ -152,8 +154,85 @@ def exchange_out(pl, O, B, Ll, nh, d, group=None):
     out_splits = [n if src % qs == pl.s else 0 for src in range(P)]         # one block per head-group owner
     recv = torch.empty(hg * n, device=O.device, dtype=O.dtype)
     send = O.reshape(-1)
-    comm_point(lambda: all_to_all_single(recv, send, out_splits, in_splits, group))
-    return recv.view(hg, Ll, B, hp, d).permute(2, 1, 0, 3, 4).reshape(B, Ll, nh, d)
+    def exchange():
+        with ops.timed("sp_a2a_o"):
+            all_to_all_single(recv, send, out_splits, in_splits, group)
+    comm_point(exchange)
+    with ops.timed("sp_unpack"):
+        return recv.view(hg, Ll, B, hp, d).permute(2, 1, 0, 3, 4).reshape(B, Ll, nh, d)
+
+
+# ---------------------------------------------------------------------------------------------- NVLink peer exchange
+class PeerExchange:
+    """The self-attention all-to-alls as direct peer stores (csrc/sp_exchange.cu) instead of NCCL: every rank maps the
+    receive buffers and flag arrays of all ranks of the group through CUDA IPC (sa_ipc_export / sa_ipc_open, handles
+    exchanged once with all_gather_object); per block the rank then runs
+        scatter_qkv -> barrier -> attention on its receive buffers -> scatter_o -> barrier -> o_recv is [B, Ll, nh, d].
+    Single buffers suffice: a peer overwrites kv/q_recv only after the second barrier of the block, which this rank
+    passes after its attention has read them, and o_recv only after the first barrier of the next block, which comes
+    after the output projection. Everything is an ordinary kernel on the current stream, so the whole step is captured
+    in one CUDA graph (no comm_point splits)."""
+
+    def __init__(self, pl, B, Ll, nh, d, device, group=None):
+        self.pl, self.shape, self.group = pl, (B, Ll, nh, d), group
+        P, hp = pl.world, pl.hp
+        bf = torch.bfloat16
+        self.kv_recv = torch.empty(P * Ll * B * 2 * hp * d, device=device, dtype=bf)
+        self.q_recv = torch.empty(len(pl.q_sources) * Ll * B * hp * d, device=device, dtype=bf)
+        self.o_recv = torch.empty(B * Ll * nh * d, device=device, dtype=bf)
+        self.sig = torch.zeros(64, device=device, dtype=torch.int32)
+        self.epoch = torch.zeros(1, device=device, dtype=torch.int32)
+        torch.cuda.synchronize(device)
+        local = (self.kv_recv, self.q_recv, self.o_recv, self.sig)
+        metas = [None] * P
+        dist.all_gather_object(metas, [ops.ipc_export(t) for t in local], group=group)
+        self._bases, ptrs = {}, [[], [], [], []]
+        with torch.cuda.device(device):                      # peer access is enabled for the device current at open time
+            for r in range(P):
+                for j in range(4):
+                    if r == pl.rank:
+                        ptrs[j].append(local[j].data_ptr())
+                        continue
+                    handle, off = metas[r][j]
+                    if (r, handle) not in self._bases:       # buffers of one peer may share a cudaMalloc segment
+                        self._bases[(r, handle)] = ops.ipc_open(handle)
+                    ptrs[j].append(self._bases[(r, handle)] + off)
+        self.kv_ptrs, self.q_ptrs, self.o_ptrs, self.sig_ptrs = ptrs
+        dist.barrier(group=group)                               # every rank has mapped every buffer before the first store
+
+    def barrier(self):
+        ops.sp_barrier(self.sig_ptrs, self.epoch, self.pl.world, self.pl.rank)
+
+    def exchange_qkv(self, qkv):
+        """qkv: local [B*Ll, 3*nh*d] rows after RMSNorm+RoPE. Returns (Q [Lq, B, hp, d], KV [L, B, 2, hp, d])."""
+        B, Ll, nh, d = self.shape
+        pl = self.pl
+        with ops.timed("sp_a2a_qkv"):
+            ops.sp_scatter_qkv(qkv, self.kv_ptrs, self.q_ptrs, B=B, Ll=Ll, heads=nh, P=pl.world, rank=pl.rank, hg=pl.hg)
+            self.barrier()
+        return (self.q_recv.view(len(pl.q_sources) * Ll, B, pl.hp, d), self.kv_recv.view(pl.world * Ll, B, 2, pl.hp, d))
+
+    def exchange_out(self, O):
+        B, Ll, nh, d = self.shape
+        pl = self.pl
+        with ops.timed("sp_a2a_o"):
+            ops.sp_scatter_o(O, self.o_ptrs, B=B, Ll=Ll, heads=nh, P=pl.world, rank=pl.rank, hg=pl.hg)
+            self.barrier()
+        return self.o_recv.view(B, Ll, nh, d)
+
+
+def _peer_exchange(model, B, Ll, nh, d, device):
+    """The model's PeerExchange for these shapes, or None when the NCCL path is selected (SA_SP_PEER=0, CPU / gloo)."""
+    import os
+    if device.type != "cuda" or os.environ.get("SA_SP_PEER", "1") == "0" or dist.get_backend(model.sp_group) != "nccl":
+        return None
+    px = getattr(model, "_sp_px", None)
+    if px is None or px.shape != (B, Ll, nh, d):
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("sequence_parallel: the peer exchange buffers must be created by an eager (warm-up) "
+                               "forward before CUDA-graph capture")
+        px = model._sp_px = PeerExchange(model._sp, B, Ll, nh, d, device, model.sp_group)
+    return px
 
 
 # ---------------------------------------------------------------------------------------------- model hooks
@@ -173,11 +252,17 @@ def self_attention(model, qkv, sa, st):
     pl = model._sp
     ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
                       grid=st["grid"], rows_per_batch=Ll, tok_offset=st["tok0"])
-    q5 = qkv.view(B, Ll, 3, nh, 128)
-    Q, KV = exchange_qkv(pl, q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], model.sp_group, kv=q5[:, :, 1:3])
+    px = _peer_exchange(model, B, Ll, nh, 128, qkv.device)
+    if px is not None:
+        Q, KV = px.exchange_qkv(qkv)
+    else:
+        q5 = qkv.view(B, Ll, 3, nh, 128)
+        Q, KV = exchange_qkv(pl, q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], model.sp_group, kv=q5[:, :, 1:3])
     with ops.timed("self_attn"):
         O = ops.flash_attn(Q.transpose(0, 1), KV[:, :, 0].transpose(0, 1), KV[:, :, 1].transpose(0, 1),
                            out=torch.empty_like(Q).transpose(0, 1))
+    if px is not None:
+        return px.exchange_out(O.transpose(0, 1))
     return exchange_out(pl, O.transpose(0, 1), B, Ll, nh, 128, model.sp_group)
 
 

@@ -1,5 +1,6 @@
-"""GPU test (-m gpu, needs >= 2 GPUs, else skipped): sequence-parallel forward over NCCL equals the single-GPU forward
-(the reference's single-GPU semantics are the oracle for SP, SURVEY.md fact #9-iii and §8c)."""
+"""GPU test (-m gpu, needs >= 2 GPUs, else skipped): the sequence-parallel forward equals the single-GPU forward (the
+reference's single-GPU semantics are the oracle for SP, SURVEY.md fact #9-iii and §8c) — with the all-to-alls as direct
+NVLink peer stores (csrc/sp_exchange.cu, the default) and over NCCL all_to_all_single (SA_SP_PEER=0)."""
 import os
 import socket
 
@@ -22,8 +23,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q_out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _worker(rank, world, port, q_out, peer):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SA_SP_PEER=peer)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -41,24 +42,33 @@ def _worker(rank, world, port, q_out):
         single = m(**kw).float()
         m.enable_multi_gpus_inference()
         sp_out = m(**kw).float()
+        again = m(**kw).float()                      # second call: receive buffers and barrier epochs are reused
         torch.cuda.synchronize()
+        assert (getattr(m, "_sp_px", None) is not None) == (peer == "1")
+        assert torch.equal(sp_out, again)
         q_out.put((rank, ((sp_out - single).norm() / single.norm()).item()))
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("peer", ["1", "0"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sp_forward_equals_single_gpu(world):
+def test_sp_forward_equals_single_gpu(world, peer):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, peer)) for r in range(world)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(300)
-        assert p.exitcode == 0
+    try:
+        for p in procs:
+            p.join(240)
+            assert p.exitcode == 0, f"rank process exit code {p.exitcode}"
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     res = dict(q.get(timeout=5) for _ in range(world))
     assert max(res.values()) < 1e-2, res
