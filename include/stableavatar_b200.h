@@ -247,6 +247,33 @@ int sa_vae_video_in(const void* x, void* out, int32_t Cx, int64_t P, int32_t Cpa
 int sa_vae_latent_out(const void* h, const void* wc, const void* bc, const void* mean, const void* stdv, void* out,
                       int32_t Cz, int64_t P, sa_stream_t stream);
 
+/* ---- fp32 mode (BASELINE config 1: fp32 weights, per-block tolerance 1e-4) ----------------------------------------
+ * A fp32 Linear runs on the bf16 tensor cores as ONE sa_gemm_bf16 over a six-fold K: both operands are split into three
+ * bf16 terms (x = x0 + x1 + x2) and laid out as [x0|x0|x1|x1|x0|x2] (pattern 0, activation side) and
+ * [w0|w1|w0|w1|w2|w0] (pattern 1, weight side), so the fp32 accumulator sums the six significant cross products
+ * (error ~2^-24). sa_f32_split3: x f32 [M, K] (row stride ld) -> out bf16 [M, 6*K_pad], columns K..K_pad zero. Call sa_gemm_bf16 on the two split
+ * operands with out_dtype f32, round_y 0 (GELU then uses libm tanhf). The rest are the fp32 forms of the elementwise
+ * steps (same reference lines as their bf16 versions): patchify/unpatchify (1B.py:972-983, 1161-1184), modulation
+ * out = x (1 + scale[b]) + shift[b] and gated residual h += y * gate[b] (1B.py:675-691; gate NULL = plain add),
+ * RMSNorm (+3-D RoPE) in place (1B.py:296-342), in-place row softmax of x * scale (1B.py:158-207), broadcast add
+ * out[i,j,:] = a[i,:] + b[j,:] (1B.py:672), CFG + Euler (pipe.py:752-754). */
+int sa_f32_split3(const void* x, int64_t ld, int64_t M, int32_t K, int32_t K_pad, void* out, int32_t pattern,
+                  sa_stream_t stream);
+int sa_f32_patchify(const void* x, const void* y, void* out, int32_t B, int32_t Cx, int32_t Cy, int32_t F, int32_t H,
+                    int32_t W, int32_t seq_len, int32_t K_pad, sa_stream_t stream);
+int sa_f32_unpatchify(const void* u, void* out, int64_t u_bs, int64_t u_ls, int32_t B, int32_t Cout, int32_t F, int32_t H,
+                      int32_t W, sa_stream_t stream);
+int sa_f32_modulate(const void* x, const void* shift, const void* scale, void* out, int64_t rows, int32_t C,
+                    int32_t rows_per_batch, int64_t mod_bs, sa_stream_t stream);
+int sa_f32_gated_add(void* h, const void* y, int64_t ldy, const void* gate, int64_t rows, int32_t C, int32_t rows_per_batch,
+                     int64_t gate_bs, sa_stream_t stream);
+int sa_f32_rmsnorm_rope(void* x, int64_t ld, const void* weight, const void* freqs, int32_t rows, int32_t C,
+                        int32_t rows_per_batch, int32_t F, int32_t H, int32_t W, float eps, sa_stream_t stream);
+int sa_f32_softmax_rows(void* x, int32_t rows, int32_t n, int64_t ld, float scale, sa_stream_t stream);
+int sa_f32_add_bcast(const void* a, const void* b, void* out, int32_t na, int32_t nb, int32_t n, sa_stream_t stream);
+int sa_f32_cfg_euler_step(const void* pred, const void* latents, void* out, void* noise_out, int64_t n, float audio_scale,
+                          float text_scale, float dsigma, const void* dsigma_dev, int32_t cfg, sa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,7 +106,12 @@ __device__ __forceinline__ float act_fn(float y) {
     return y;
   }
 }
-__device__ __forceinline__ float act_rt(float y, int act) {
+__device__ __forceinline__ float act_rt(float y, int act, bool exact) {
+  if (exact && act == 1) {  // fp32 mode (round_y == 0): libm tanhf instead of tanh.approx (2^-11 relative error)
+    const float u = y * fmaf(0.7978845608028654f * 0.044715f, y * y, 0.7978845608028654f);
+    return 0.5f * y * (1.0f + tanhf(u));
+  }
+  if (exact && act == 2) return y / (1.0f + expf(-y));
   return act == 1 ? act_fn<1>(y) : (act == 2 ? act_fn<2>(y) : (act == 3 ? act_fn<3>(y) : y));
 }
 
@@ -313,7 +318,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (p.bias) y += load1(p.bias, p.bias_dtype, n);
             if (p.round_y) y = bf16_round(y);
             if (p.act) {
-              y = act_rt(y, p.act);
+              y = act_rt(y, p.act, !p.round_y);
               if (p.round_y) y = bf16_round(y);
             }
             if (p.res_mode) {

@@ -110,7 +110,8 @@ class WanI2VTalkingInferenceLongPipeline:
         """One window of one step (pipe.py:730-754): DiT forward on the CFG batch, CFG combine, Euler update.
         latents [1,16,f,h,w] bf16 -> new latents (bf16)."""
         tc = getattr(self.transformer, "teacache", None)
-        if self.use_cuda_graphs and tc is None and getattr(self.transformer, "hooks", None) is None:
+        fp32 = getattr(self.transformer, "dtype", None) == torch.float32      # fp32 parity mode: eager, fp32 CFG + Euler
+        if self.use_cuda_graphs and tc is None and not fp32 and getattr(self.transformer, "hooks", None) is None:
             key = (tuple(latents.shape), tuple(vocal_embeddings.shape), seq_len, clip_length, float(text_guide_scale or 0),
                    float(audio_guide_scale or 0), do_cfg, y.data_ptr(), clip_context.data_ptr(),
                    tuple(p.data_ptr() for p in prompt_embeds))
@@ -126,9 +127,13 @@ class WanI2VTalkingInferenceLongPipeline:
         noise_pred = self.transformer(x=x, context=prompt_embeds, t=tt, seq_len=seq_len, y=y[:, :, :latents.size(2)],
                                       clip_fea=clip_context, vocal_embeddings=vocal_embeddings,
                                       is_clip_level_modeling=False, video_sample_n_frames=clip_length)
-        return ops.cfg_euler_step(noise_pred.contiguous(), latents.contiguous(), dsigma,
-                                  audio_scale=float(audio_guide_scale or 0.0), text_scale=float(text_guide_scale or 0.0),
-                                  cfg=do_cfg)
+        if fp32:
+            from . import fp32_mode
+            step = fp32_mode.cfg_euler_step
+        else:
+            step = ops.cfg_euler_step
+        return step(noise_pred.contiguous(), latents.contiguous(), dsigma, audio_scale=float(audio_guide_scale or 0.0),
+                    text_scale=float(text_guide_scale or 0.0), cfg=do_cfg)
 
     @torch.no_grad()
     def denoise(self, latents_all, prompt_embeds, clip_context, y, vocal_embeddings_fn, *, num_inference_steps,
@@ -155,7 +160,7 @@ class WanI2VTalkingInferenceLongPipeline:
                 idx = [ii % n_lat for ii in range(ws, we)]
                 latents = latents_all[:, :, idx].clone()
                 if (ws, we) not in audio_cache:
-                    v = vocal_embeddings_fn(ws, we, we == infer_length).to(dev, torch.bfloat16)
+                    v = vocal_embeddings_fn(ws, we, we == infer_length).to(dev, latents_all.dtype)
                     audio_cache[(ws, we)] = torch.cat([torch.zeros_like(v), v, v]) if do_cfg else v
                 latents = self.denoise_step(latents, t, self.scheduler.dsigma_at(i), prompt_embeds, clip_context, y,
                                             audio_cache[(ws, we)], seq_len=seq_len, clip_length=clip_length,
@@ -166,7 +171,7 @@ class WanI2VTalkingInferenceLongPipeline:
                     s_idx = [ii % latents.shape[2] for ii in range(overlap_window_length)]
                     e_idx = [ii % n_lat for ii in range(prev_end - overlap_window_length, prev_end)]
                     latents[:, :, s_idx] = latents[:, :, s_idx] * ow + pred_latents[:, :, e_idx] * (1 - ow)
-                latents = latents.to(torch.bfloat16)
+                latents = latents.to(latents_all.dtype)
                 pred_latents[:, :, [(ws + k) % n_lat for k in range(latents.size(2))]] = latents
             latents_all = pred_latents
             if callback is not None:

@@ -7,8 +7,9 @@ is_clip_level_modeling, video_sample_n_frames)` signature and error behaviour, `
 `enable_teacache / disable_teacache / enable_riflex / disable_riflex / enable_multi_gpus_inference`.
 
 The modules below only hold parameters; all arithmetic goes through the C-ABI library (stableavatar_b200.ops) and
-follows the reference's bf16 autocast rounding points. bf16 parameters on a CUDA device are
-required; there is no CPU or eager fallback.
+follows the reference's bf16 autocast rounding points. bf16 parameters on a CUDA device select
+the production path; float32 parameters select the fp32 parity mode (fp32_mode.py, BASELINE config 1, 1e-4 per block);
+there is no CPU or eager fallback.
 """
 from __future__ import annotations
 
@@ -284,8 +285,8 @@ class WanTransformer3DFantasyModel(nn.Module):
             return self._prep
         w = self.patch_embedding.weight
         if w.dtype != torch.bfloat16 or not w.is_cuda:
-            raise RuntimeError("WanTransformer3DFantasyModel (B200): parameters must be bf16 on a CUDA device "
-                               "(model.to('cuda', torch.bfloat16)); there is no CPU / fp32 fallback path")
+            raise RuntimeError("WanTransformer3DFantasyModel (B200): parameters must be bf16 (or float32 for the fp32 "
+                               "parity mode) on a CUDA device; there is no CPU fallback path")
         cat = lambda *ts: torch.cat(ts).contiguous()  # noqa: E731
         blocks = []
         for b in self.blocks:
@@ -316,6 +317,11 @@ class WanTransformer3DFantasyModel(nn.Module):
                 is_clip_level_modeling=False, video_sample_n_frames=81):
         if self.model_type == "i2v":
             assert clip_fea is not None and y is not None
+        if self.dtype == torch.float32:                   # fp32 mode (BASELINE config 1): split-bf16 GEMMs, see fp32_mode.py
+            from . import fp32_mode
+            return fp32_mode.forward(self, x, t, context, seq_len, clip_fea=clip_fea, y=y, cond_flag=cond_flag,
+                                     vocal_embeddings=vocal_embeddings, is_clip_level_modeling=is_clip_level_modeling,
+                                     video_sample_n_frames=video_sample_n_frames)
         p = self._prepare()
         dev, bf = self.device, torch.bfloat16
         C, nh = self.dim, self.num_heads
