@@ -39,6 +39,7 @@ int sa_device_sm_count(void);
  *   out = y                               res_mode 0
  *       = res + y                         res_mode 1   (1B.py:684  x + cross_attn(...))
  *       = res + bf16(y * gate[row/rows_per_batch, n])   res_mode 2   (1B.py:679,691  x + y * e[k])
+ *   res_mode 3: res is added BEFORE the activation, out = act(acc + bias + res) — K-chunked accumulation of the fp32 mode
  * A, W: bf16 (lda/ldw = row strides in elements, multiples of 8). bias: bf16/f32 [N] or NULL. gate: bf16 [*, N] with
  * row stride gate_ld. res/out: bf16 or f32 per res_dtype/out_dtype with row strides ldr/ldc. res may alias out.
  */

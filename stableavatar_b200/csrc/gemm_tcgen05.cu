@@ -316,12 +316,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (n >= p.N) break;
             float y = __uint_as_float(r[j]);
             if (p.bias) y += load1(p.bias, p.bias_dtype, n);
+            if (p.res_mode == 3) y += load1(p.res, p.res_dtype, (long long)row * p.ldr + n);  // K-chunked accumulation
             if (p.round_y) y = bf16_round(y);
             if (p.act) {
               y = act_rt(y, p.act, !p.round_y);
               if (p.round_y) y = bf16_round(y);
             }
-            if (p.res_mode) {
+            if (p.res_mode == 1 || p.res_mode == 2) {
               const float rs = load1(p.res, p.res_dtype, (long long)row * p.ldr + n);
               if (p.res_mode == 2) {
                 float t = y * load1(p.gate, SA_BF16, gate_row + n);
@@ -385,7 +386,7 @@ extern "C" int sa_gemm_bf16(const sa_gemm_args* a, sa_stream_t stream_) {
     set_error("sa_gemm_bf16: gated residual needs gate and rows_per_batch > 0");
     return SA_ERR_BAD_ARG;
   }
-  if (a->act < 0 || a->act > 3 || a->res_mode < 0 || a->res_mode > 2) {
+  if (a->act < 0 || a->act > 3 || a->res_mode < 0 || a->res_mode > 3) {
     set_error("sa_gemm_bf16: bad act/res_mode");
     return SA_ERR_BAD_ARG;
   }
@@ -406,7 +407,7 @@ extern "C" int sa_gemm_bf16(const sa_gemm_args* a, sa_stream_t stream_) {
     if (rc) return rc;
   }
   // Fast path: bf16 everywhere, autocast rounding, 16-byte aligned rows.
-  const bool fast = a->out_dtype == SA_BF16 && a->round_y && a->N % 8 == 0 && a->ldc % 8 == 0 &&
+  const bool fast = a->out_dtype == SA_BF16 && a->round_y && a->res_mode != 3 && a->N % 8 == 0 && a->ldc % 8 == 0 &&
                     (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (!a->bias || a->bias_dtype == SA_BF16) &&
                     (!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) &&
                     (a->res_mode == 0 || (a->res_dtype == SA_BF16 && a->ldr % 8 == 0 &&

@@ -34,23 +34,44 @@ def split3(x, pattern):
 
 
 _W_CACHE = {}
+KC = 256     # K elements per GEMM launch: the tensor core truncates when it adds into the fp32 accumulator (measured
+#              ~3e-8 relative per K=16 step, same sign, so the error grows linearly with K: 1.7e-5 at K = 1536); chunks
+#              of 256 are accumulated across launches by the epilogue's round-to-nearest fp32 add instead (~2e-6 total).
+
+
+def _chunks(K):
+    return [(k0, min(k0 + KC, K)) for k0 in range(0, K, KC)]
 
 
 def split_weight(w):
-    """Weight-side split of a parameter, cached until the parameter's storage or version changes."""
+    """Weight-side split of a parameter per K chunk, cached until the parameter's storage or version changes."""
     key = (w.data_ptr(), tuple(w.shape), w._version)
     hit = _W_CACHE.get(id(w))
     if hit is None or hit[0] != key:
-        hit = (key, split3(w.reshape(w.shape[0], -1), 1))
+        w2 = w.reshape(w.shape[0], -1)
+        hit = (key, [split3(w2[:, k0:k1], 1) for k0, k1 in _chunks(w2.shape[1])])
         _W_CACHE[id(w)] = hit
     return hit[1]
 
 
+def matmul_nt(x, w_chunks, bias=None, act=ops.ACT_NONE, out=None, accumulate=False):
+    """out (+)= act(x @ w^T + bias) for fp32 x [M, K] and the K-chunked weight-side splits of w [N, K]."""
+    N = w_chunks[0].shape[0]
+    if out is None:
+        out = torch.empty(x.shape[0], N, device=x.device, dtype=F32)
+        accumulate = False
+    ch = _chunks(x.shape[1])
+    assert len(ch) == len(w_chunks)
+    for i, (k0, k1) in enumerate(ch):
+        last = i == len(ch) - 1
+        ops.gemm(split3(x[:, k0:k1], 0), w_chunks[i], bias if i == 0 else None, act=act if last else ops.ACT_NONE, out=out,
+                 res=out if (i > 0 or accumulate) else None, res_before_act=True, round_y=False)
+    return out
+
+
 def linear(x, w, bias=None, act=ops.ACT_NONE, w_split=None):
     """fp32 x [M, K] @ w[N, K]^T (+ bias) (+ activation) -> fp32 [M, N]."""
-    ws = split_weight(w) if w_split is None else w_split
-    out = torch.empty(x.shape[0], ws.shape[0], device=x.device, dtype=F32)
-    return ops.gemm(split3(x, 0), ws, bias, act=act, out=out, round_y=False)
+    return matmul_nt(x, split_weight(w) if w_split is None else w_split, bias, act)
 
 
 def modulate(x, shift, scale, rows_per_batch, mod_bs):
@@ -139,11 +160,11 @@ def attention(q, k, v, out=None, accumulate=False):
     s = torch.empty(Lq, ldp, device=q.device, dtype=F32)
     for b in range(B):
         for h in range(H):
-            ops.gemm(split3(q[b, :, h], 0), split3(k[b, :, h], 1), out=s[:, :Lk], round_y=False)
+            kh = k[b, :, h]
+            matmul_nt(q[b, :, h], [split3(kh[:, k0:k1], 1) for k0, k1 in _chunks(D)], out=s[:, :Lk])
             softmax_rows_(s[:, :Lk], D ** -0.5)
             vt = v[b, :, h].t().contiguous()                                 # [D, Lk]: layout change only
-            o = out[b, :, h]                                                 # [Lq, D] view, row stride H * D
-            ops.gemm(split3(s[:, :Lk], 0), split3(vt, 1), out=o, res=o if accumulate else None, round_y=False)
+            matmul_nt(s[:, :Lk], [split3(vt[:, k0:k1], 1) for k0, k1 in _chunks(Lk)], out=out[b, :, h], accumulate=accumulate)
     return out
 
 
@@ -220,7 +241,7 @@ def forward(model, x, t, context, seq_len, clip_fea=None, y=None, cond_flag=True
         w_pad = torch.zeros(C_, A.shape[-1], device=dev, dtype=F32)
         w_pad[:, :K] = w_pe
         w_pe = w_pad
-    h = linear(A.view(B * Lt, -1), w_pe, model.patch_embedding.bias, w_split=split3(w_pe.contiguous(), 1))
+    h = linear(A.view(B * Lt, -1), w_pe, model.patch_embedding.bias, w_split=[split3(w_pe.contiguous(), 1)])
     if Lt > Lv:
         h.view(B, Lt, C_)[:, Lv:].zero_()
 

@@ -39,7 +39,7 @@ def _need_cuda(*ts):
 
 
 def gemm(a, w, bias=None, *, out=None, act=ACT_NONE, res=None, gate=None, gate_ld=0, rows_per_batch=0, round_y=True,
-         out_dtype=torch.bfloat16):
+         out_dtype=torch.bfloat16, res_before_act=False):
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) — see sa_gemm_bf16. a may be a row-strided 2-D view."""
     _need_cuda(a, w)
     assert a.dim() == 2 and w.dim() == 2 and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -55,7 +55,7 @@ def gemm(a, w, bias=None, *, out=None, act=ACT_NONE, res=None, gate=None, gate_l
                    ldr=res.stride(0) if res is not None else 0, gate_ld=gate_ld, M=M, N=N, K=K,
                    bias_dtype=L.dt(bias) if bias is not None else 0, out_dtype=L.dt(out),
                    res_dtype=L.dt(res) if res is not None else 0, act=act,
-                   res_mode=0 if res is None else (2 if gate is not None else 1), round_y=int(round_y),
+                   res_mode=0 if res is None else (3 if res_before_act else (2 if gate is not None else 1)), round_y=int(round_y),
                    rows_per_batch=rows_per_batch)
     L.check(L.lib().sa_gemm_bf16(C.byref(g), L.stream_ptr()), "sa_gemm_bf16")
     return out
