@@ -130,3 +130,25 @@ def test_fp32_denoise_step_vs_oracle():
     u, d, c = pred[0], pred[1], pred[2]
     want = inp["x"][0] + (-0.02) * (u + 5.0 * (d - u) + 3.0 * (c - d))
     assert new.dtype == torch.float32 and rel(new[0], want) < TOL
+
+
+def test_config1_grid_480x832x5_fp32_full_width_vs_oracle():
+    """BASELINE config 1 — 480x832, 5 frames (L = 2 x 30 x 52 = 3120), fp32, CFG batch 3 — at the full 1.3B width (dim 1536,
+    12 heads, ffn 8960: 35 K-chunks in the FFN down projection) with 2 of the 30 layers, against the fp32 CPU oracle."""
+    from oracle import dit as O
+    from stableavatar_b200.wan_transformer3d import WanTransformer3DFantasyModel
+    cfg = dict(synth.DIT_1_3B, num_layers=2, text_dim=256, text_len=32)
+    sd = synth.dit_state_dict(cfg)
+    m = WanTransformer3DFantasyModel(**{k: cfg[k] for k in KEYS})
+    m.load_state_dict(sd, strict=True)
+    m = m.to("cuda", torch.float32)
+    inp = synth.dit_inputs(cfg, frames=5, height=480, width=832, seed=7)
+    out, hooks = run(m, inp)
+    rh = {}
+    with torch.no_grad():
+        ref = O.dit_forward(sd, cfg, inp["x"], inp["t"], inp["context"], inp["seq_len"], inp["clip_fea"], inp["y"],
+                            inp["vocal_embeddings"], 5, hooks=rh)
+    assert out.shape == (3, 16, 2, 60, 104)
+    for i in range(2):
+        assert rel(hooks[f"block{i}"], rh[f"block{i}"]) < TOL, i
+    assert rel(out, ref) < TOL
