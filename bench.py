@@ -268,24 +268,36 @@ def run_b200(args):
     s_per_step = ms.item() / 1e3 / args.steps
     s_e2e = ms_e2e.item() / 1e3 / args.steps
 
-    vae_s = None
-    if rank == 0 and not args.no_vae:
-        # BASELINE "e2e s/clip": the clip = 50 denoise steps + one Wan VAE decode of the final latents (pipe.py:793-799)
+    def vae_decode_time():
+        """BASELINE "e2e s/clip": the clip = 50 denoise steps + one Wan VAE decode of the final latents (pipe.py:793-799).
+        One GPU: plain decode. N > 1: the decoder runs as a pipeline over the N ranks (bit-identical frames,
+        AutoencoderKLWan.enable_multi_gpus_decode); time = max over ranks."""
         from stableavatar_b200.wan_vae import AutoencoderKLWan
         vae = AutoencoderKLWan()
         vae.load_state_dict(synth.vae_state_dict(), strict=True)
         vae = vae.to(dev)
+        if world > 1:
+            vae.enable_multi_gpus_decode()
         z = synth.det_normal("bench_z", (1, 16, F_lat, h, w)).to(dev)
         vae.decode(z[:, :, :2])                              # warm-up: operand preparation
-        torch.cuda.synchronize()
+        barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         video = vae.decode(z).sample
         ev1.record()
-        torch.cuda.synchronize()
-        vae_s = ev0.elapsed_time(ev1) / 1e3
+        barrier()
         assert video.shape == (1, 3, args.frames, args.height, args.width)
-        del vae, video
+        tv = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        return tv.item() / 1e3
+
+    def emit(vae_s):
+        if rank == 0:
+            line["config"]["vae_decode_s"] = vae_s
+            line["config"]["clip_s"] = None if vae_s is None else 50 * s_per_step + vae_s
+            print(json.dumps(line), flush=True)
+
     if rank == 0:
         peaks = load_peaks()
         total_flops, attn_flops_per_launch = step_flops(cfg, L)
@@ -304,12 +316,13 @@ def run_b200(args):
                        "step_tflop": total_flops / 1e12,
                        "step_tflops_achieved": total_flops / s_per_step / 1e12 / world,
                        "bf16_peak_frac_step": total_flops / s_per_step / 1e12 / world / peaks["bf16"],
-                       "launch_mode": "eager" if args.no_graph else "cuda-graph replay (value, e2e; NCCL calls eager between graph segments); kernel timing and "
+                       "launch_mode": "eager" if args.no_graph else "cuda-graph replay (value, e2e; under sequence parallelism the self-attention exchange is peer-store "
+                                      "kernels inside the graph, one eager NCCL all-gather per step); kernel timing and "
                                       "gpu_launches from an eager pass of the same steps",
                        "eager_ms_per_step": ms_eager / args.steps, "kernel_time_share": shares,
-                       "vae_decode_s": vae_s, "clip_s": None if vae_s is None else 50 * s_per_step + vae_s,
-                       "clip_s_note": "50 denoise steps x value + one VAE decode (21x60x104 latent -> 81x480x832), "
-                                      "decode on one GPU (replicas only)"},
+                       "vae_decode_s": None, "clip_s": None,
+                       "clip_s_note": "50 denoise steps x value + one VAE decode (21x60x104 latent -> 81x480x832)"
+                                      + (f", decoder pipelined over the {world} GPUs (bit-identical frames)" if world > 1 else "")},
             "roofline": {"kernel": "flash_attn_d128_kernel (self-attention)", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"] if achieved else None,
                          "traffic": SELF_ATTN_DRAM_BYTES_B3 / world if (args.frames, args.height, args.width) == (81, 480, 832) else None,
@@ -326,7 +339,25 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": per_block * cfg["num_layers"] * 3, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"1 WanAttentionBlock of the oracle port (fp32) at L={L}, B=1 measured "
                                               f"{per_block:.2f} s; extrapolated x{cfg['num_layers']} blocks x3 CFG samples"}
-        print(json.dumps(line), flush=True)
+    # The VAE stage runs last and under a watchdog: if the multi-GPU decode does not finish, the step line is still printed.
+    if args.no_vae:
+        emit(None)
+    else:
+        import threading
+
+        def give_up():
+            emit(None)
+            os._exit(0)
+        timer = threading.Timer(240.0, give_up)
+        timer.daemon = True
+        timer.start()
+        try:
+            vae_s = vae_decode_time()
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] VAE decode stage failed on rank {rank}: {exc!r}", file=sys.stderr, flush=True)
+            vae_s = None
+        timer.cancel()
+        emit(vae_s)
     if world > 1:
         dist.destroy_process_group()
 
