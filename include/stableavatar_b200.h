@@ -77,6 +77,29 @@ typedef struct {
 } sa_attn_args;
 int sa_flash_attn_d128(const sa_attn_args* args, sa_stream_t stream);
 
+/* The three cross-attentions of WanI2VTalkingCrossAttention (1B.py:534-605) in one launch: out (+)= sum over the key sets
+ * of softmax(q K_s^T * scale) V_s, each partial result rounded to bf16 before the bf16 add (set order = argument order),
+ * q loaded once. q/out: bf16 [batch, q_len, heads, 128] views as in sa_attn_args. A set is [batch, kv_total, heads, 128]
+ * (strides k_bs/k_ls, v_bs/v_ls). windowed = 0: all kv_len = kv_total keys. windowed = 1 (audio, 1B.py:575-586): the keys
+ * are kv_total / kv_len consecutive windows of kv_len keys and query row r attends only to window
+ * (tok_offset + r) / rows_per_group; requires (255 / rows_per_group + 2) * kv_len <= 64. */
+typedef struct {
+  const void* k;
+  const void* v;
+  int64_t k_bs, k_ls, v_bs, v_ls;
+  int32_t kv_len, kv_total, windowed;
+} sa_cross_attn_set;
+typedef struct {
+  const void* q;
+  void* out;
+  int64_t q_bs, q_ls, o_bs, o_ls;
+  int32_t batch, heads, q_len, n_sets;
+  float scale;
+  int32_t accumulate, rows_per_group, tok_offset;
+  sa_cross_attn_set set[3];
+} sa_cross_attn_args;
+int sa_cross_attn3_d128(const sa_cross_attn_args* args, sa_stream_t stream);
+
 /* Same contract for a handful of queries per (batch, head) and any head_dim % 8 == 0: the audio adapter's
  * cross-attention, 15 audio tokens x 1560 video tokens x 8 heads of 192
  * (wan/models/vocal_projector_fantasy_1B.py:259-277; SDPA branch :178-203), and 8 heads of 640 for the 14B adapter

@@ -1,0 +1,510 @@
+// attn_cross_tcgen05.cu — the three cross-attentions of a DiT block in ONE launch (sm_100a, head_dim 128).
+//
+// WanI2VTalkingCrossAttention (wan/models/wan_fantasy_transformer3d_1B.py:534-605) sums three softmax attentions that
+// share the query: text (512 keys), CLIP image (257 keys) and audio (15 keys of the latent frame's audio window, paired
+// with the token group by q.view(b * G, -1, n, d), :575-586). As three launches of the self-attention kernel each one
+// re-reads Q (302 MB at B = 3) and read-modify-writes O; here a CTA loads its two 128-row Q tiles into TMEM once and
+// walks the key sets back to back through the same decoupled pipeline as attn_v8_tcgen05.cu (global step counter, so
+// all mbarrier phases simply keep running), finishing each set with the usual O / l epilogue that adds into the
+// output rows it wrote a few microseconds earlier (L2 hits). Per-set rounding and order (text, image, audio; every
+// partial result rounded to bf16 before the bf16 add) are those of the three-launch path, so results are bit-identical.
+//
+// The audio set is one 64-key step: the keys of the (at most 64 / A) consecutive windows that the CTA's 256 rows can
+// touch are loaded together and every row masks the step down to its own window [ (g - g0) A, (g - g0) A + A ), with
+// g = (tok_offset + row) / rows_per_group — which also covers token shards of the sequence-parallel path.
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "../../include/stableavatar_b200.h"
+#include "sa_host.h"
+#include "sa_ptx.cuh"
+
+namespace sa {
+namespace attnx {
+
+constexpr int BQ = 128, SUB = 64, D = 128;
+constexpr int STAGES = 4;
+constexpr int KV_PANEL = SUB * 128;          // 64 rows x 128 B = 8 KB
+constexpr int KV_TILE = 2 * KV_PANEL;        // [64 keys x 128 d] = 16 KB
+constexpr int STAGE_BYTES = 2 * KV_TILE;     // K + V
+constexpr int P_BYTES = BQ * 128;            // [128 rows x 64 keys] bf16 = 16 KB
+constexpr int NUM_THREADS = 352;   // 8 softmax warps, TMA producer, one MMA-issuing warp per Q tile
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * P_BYTES + 256 + 1024;
+constexpr float kRescaleThreshold = 8.0f;
+
+constexpr int MAX_SETS = 3;
+struct Params {
+  const __nv_bfloat16* q;
+  __nv_bfloat16* out;
+  long long q_bs, q_ls, o_bs, o_ls;
+  int q_len;
+  float scale_log2;
+  int accumulate;
+  int n_sets;
+  int kv_len[MAX_SETS];     // keys of the set (windowed set: keys per window)
+  int windowed[MAX_SETS];   // 1: per-row window of kv_len keys inside one 64-key step
+  int rows_per_group, tok_offset;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant__ CUtensorMap tv0,
+                  const __grid_constant__ CUtensorMap tk1, const __grid_constant__ CUtensorMap tv1,
+                  const __grid_constant__ CUtensorMap tk2, const __grid_constant__ CUtensorMap tv2, const Params p) {
+  constexpr int kPolyPairs = 0;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sKV = smem;                                   // [STAGES][K tile | V tile]
+  uint8_t* sP = smem + STAGES * STAGE_BYTES;             // [2 q tiles][2 buffers][P_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * P_BYTES);
+  uint64_t* kv_full = bars;                 // [STAGES]
+  uint64_t* kv_empty = bars + STAGES;       // [STAGES]
+  uint64_t* s_full = bars + 2 * STAGES;     // [2]  S_i(u) complete in TMEM
+  uint64_t* s_cons = s_full + 2;            // [2]  softmax i has S_i(u) in registers
+  uint64_t* p_full = s_cons + 2;            // [2 tiles][2 P buffers]  P_i(u) in shared memory (and O_i rescaled if needed).
+                                            // One barrier per P buffer: a softmax warpgroup may finish steps u and u+1
+                                            // before the MMA warp (held up by the other tile) consumes P_i(u); with a
+                                            // single barrier those two completions would alias in the phase parity.
+  uint64_t* pv_done = p_full + 4;           // [2]  one completion per PV_i(u)
+  uint64_t* o_final = pv_done + 2;          // [2]
+  uint64_t* q_ready = o_final + 2;          // [1]  Q tiles stored in TMEM
+  uint64_t* o_free = q_ready + 1;           // [2]  the epilogue of a set has read O_i: the next set may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * BQ);
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  auto n_sub_of = [&](int si) { return p.windowed[si] ? 1 : (p.kv_len[si] + SUB - 1) / SUB; };
+  int n_total = 0;
+  for (int si = 0; si < p.n_sets; ++si) n_total += n_sub_of(si);
+  const int g0 = (p.tok_offset + q0) / p.rows_per_group;   // first window any row of this CTA can belong to
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tk0);
+    tma_prefetch_desc(&tv0);
+  }
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&kv_full[s], 1);
+        mbar_init(&kv_empty[s], 2);   // one tcgen05.commit per MMA warp
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&s_cons[i], 4);
+        mbar_init(&pv_done[i], 1);
+        mbar_init(&o_final[i], 1);
+        mbar_init(&o_free[i], 4);
+      }
+      for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
+      mbar_init(q_ready, 8);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------ TMA producer: {K, V} 64-key tiles
+    if (elect_one()) {  // elect.sync: single active lane is known to ptxas -> no R2UR waterfall per UTCHMMA / UTMALDG
+      int U = 0;
+      for (int si = 0; si < p.n_sets; ++si) {
+        const CUtensorMap* tk = si == 0 ? &tk0 : (si == 1 ? &tk1 : &tk2);
+        const CUtensorMap* tv = si == 0 ? &tv0 : (si == 1 ? &tv1 : &tv2);
+        const int row0 = p.windowed[si] ? g0 * p.kv_len[si] : 0;
+        const int ns = n_sub_of(si);
+        for (int u = 0; u < ns; ++u, ++U) {
+          const int s = U % STAGES;
+          const uint32_t ph = (U / STAGES) & 1;
+          mbar_wait(&kv_empty[s], ph ^ 1, 0x9100 | s);
+          mbar_arrive_expect_tx(&kv_full[s], STAGE_BYTES);
+          uint8_t* st = sKV + s * STAGE_BYTES;
+          tma_load_4d(st, tk, &kv_full[s], 0, row0 + u * SUB, head, b);
+          tma_load_4d(st + KV_PANEL, tk, &kv_full[s], 64, row0 + u * SUB, head, b);
+          tma_load_4d(st + KV_TILE, tv, &kv_full[s], 0, row0 + u * SUB, head, b);
+          tma_load_4d(st + KV_TILE + KV_PANEL, tv, &kv_full[s], 64, row0 + u * SUB, head, b);
+        }
+      }
+    }
+  } else if (warp == 9 || warp == 10) {
+    // ------------------------------------------------------------ MMA issuers: one warp per Q tile, so that the next
+    // score tile of a Q tile is issued the moment its softmax warpgroup has consumed the current one, whatever the
+    // other tile is doing (a single issuer serving both tiles in a fixed order parks on the other tile's P).
+    if (elect_one()) {
+      const int i = warp - 9;
+      const uint32_t idesc_qk = umma_idesc_bf16(BQ, SUB, 0, 0);  // A = Q (TMEM), B = 64 keys of K (K-major)
+      const uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);    // A = P (smem, K-major), B = V (MN-major)
+      auto issue_S = [&](int u) {
+        const uint32_t ka = smem_u32(sKV + (u % STAGES) * STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * KV_PANEL + (k & 3) * 32;
+          umma_ts(tmem_base + 128 + i * SUB, tmem_base + i * 64 + k * 8, umma_smem_desc(ka + off, 16, 1024, kSwz128),
+                  idesc_qk, k != 0);
+        }
+        umma_commit(&s_full[i]);
+      };
+      auto issue_PV = [&](int u, bool first) {
+        const uint32_t va = smem_u32(sKV + (u % STAGES) * STAGE_BYTES + KV_TILE);
+        const uint32_t pa = smem_u32(sP + (i * 2 + (u & 1)) * P_BYTES);
+#pragma unroll
+        for (int k = 0; k < SUB / 16; ++k) {
+          umma_ss(tmem_base + 256 + i * 128, umma_smem_desc(pa + k * 32, 16, 1024, kSwz128),
+                  umma_smem_desc(va + k * 2048, KV_PANEL, 1024, kSwz128), idesc_pv, (!first || k != 0) ? 1u : 0u);
+        }
+        umma_commit(&pv_done[i]);
+      };
+      mbar_wait(q_ready, 0, 0x9300);
+      mbar_wait(&kv_full[0], 0, 0x9310);
+      tc_fence_after();
+      issue_S(0);
+      int U = 0;
+      for (int si = 0; si < p.n_sets; ++si) {
+        const int ns = n_sub_of(si);
+        for (int u = 0; u < ns; ++u, ++U) {
+          if (U + 1 < n_total) {
+            mbar_wait(&kv_full[(U + 1) % STAGES], ((U + 1) / STAGES) & 1, 0x9320 | ((U + 1) % STAGES));
+            mbar_wait(&s_cons[i], U & 1, 0x9330 | i);   // S_i(U) is in the softmax registers: its columns are free
+            tc_fence_after();
+            issue_S(U + 1);
+          }
+          mbar_wait(&p_full[i * 2 + (U & 1)], (U >> 1) & 1, 0x9340 | (i * 2 + (U & 1)));
+          if (u == 0 && si > 0) mbar_wait(&o_free[i], (si - 1) & 1, 0x9350 | i);   // previous set's O has been read out
+          tc_fence_after();
+          issue_PV(U, u == 0);
+          if (u == ns - 1) umma_commit(&o_final[i]);
+          umma_commit(&kv_empty[U % STAGES]);   // this tile is done with K(U), V(U)
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warpgroups (one thread per query row)
+    const int i = warp >> 2;  // Q tile
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // row inside the tile
+    const uint32_t lane_sel = uint32_t(quarter * 32) << 16;
+    const uint32_t tQ = tmem_base + lane_sel + i * 64;
+    const uint32_t tS = tmem_base + lane_sel + 128 + i * SUB;
+    const uint32_t tO = tmem_base + lane_sel + 256 + i * 128;
+    const int row = q0 + i * BQ + r;
+    const bool row_ok = row < p.q_len;
+    uint8_t* p_row0 = sP + i * 2 * P_BYTES + r * 128;
+
+    // ---- Q row -> TMEM (A operand layout: lane = row, column c holds elements 2c, 2c+1)
+    {
+      const uint4* qp = reinterpret_cast<const uint4*>(p.q + (long long)b * p.q_bs + (long long)(row_ok ? row : 0) * p.q_ls + head * D);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t w[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 v = row_ok ? qp[h * 8 + c] : make_uint4(0, 0, 0, 0);
+          w[c * 4] = v.x; w[c * 4 + 1] = v.y; w[c * 4 + 2] = v.z; w[c * 4 + 3] = v.w;
+        }
+        tmem_st_x32(tQ + h * 32, w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_ready);
+    }
+
+    const float c = p.scale_log2;
+    const uint64_t c2 = pack_f32x2(c, c);
+    float m_ref = 0.f;
+    uint64_t lsum2 = pack_f32x2(0.f, 0.f), lsum2b = pack_f32x2(0.f, 0.f);  // two independent row-sum chains
+
+    // U: global step (barrier phases, P buffer), u: step inside the current set, MASK: 0 none, 1 ragged tail, 2 window
+    auto step = [&](int U, int u, int kv_len, auto mask_tag) {
+      constexpr int MASK = decltype(mask_tag)::value;
+      mbar_wait(&s_full[i], U & 1, 0x9400 | i);
+      tc_fence_after();
+      uint32_t s[SUB];
+      {
+        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+        tmem_ld_x32(tS, s0);
+        tmem_ld_x32(tS + 32, s1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_cons[i]);   // the MMA warp may overwrite S_i with the next step's scores
+      if constexpr (MASK == 1) {
+        const int valid = kv_len - u * SUB;
+#pragma unroll
+        for (int t = 0; t < SUB; ++t)
+          if (t >= valid) s[t] = 0xff800000u;  // -inf
+      } else if constexpr (MASK == 2) {
+        const int lo = ((p.tok_offset + (row_ok ? row : q0)) / p.rows_per_group - g0) * kv_len, hi = lo + kv_len;
+#pragma unroll
+        for (int t = 0; t < SUB; ++t)
+          if (t < lo || t >= hi) s[t] = 0xff800000u;  // keys of other windows
+      }
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
+#pragma unroll
+      for (int t = 4; t < SUB; t += 8) {
+        mx0 = max3(mx0, __uint_as_float(s[t]), __uint_as_float(s[t + 1]));
+        mx1 = max3(mx1, __uint_as_float(s[t + 2]), __uint_as_float(s[t + 3]));
+        if (t + 4 < SUB) {
+          mx2 = max3(mx2, __uint_as_float(s[t + 4]), __uint_as_float(s[t + 5]));
+          mx3 = max3(mx3, __uint_as_float(s[t + 6]), __uint_as_float(s[t + 7]));
+        }
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+
+      float alpha = 1.0f;
+      bool need = false;
+      if (u == 0) {
+        m_ref = mx;
+      } else if ((mx - m_ref) * c > kRescaleThreshold) {
+        alpha = ex2_approx((m_ref - mx) * c);
+        m_ref = mx;
+        need = true;
+      }
+      // The P panel is double-buffered: P_i(u-2) V completed before S_i(u) did (issue order), so buffer u&1 is free.
+      if (__any_sync(0xffffffffu, need)) {
+        // P_i(u-1) V may still be accumulating into O_i: wait for it before rescaling (u >= 1 here).
+        mbar_wait(&pv_done[i], (U - 1) & 1, 0x9450 | i);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t o[32];
+          tmem_ld_x32(tO + cc * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
+          tmem_st_x32(tO + cc * 32, o);
+        }
+        tmem_st_wait();
+        float l_lo, l_hi;
+        unpack_f32x2(lsum2, l_lo, l_hi);
+        lsum2 = pack_f32x2(l_lo * alpha, l_hi * alpha);
+        unpack_f32x2(lsum2b, l_lo, l_hi);
+        lsum2b = pack_f32x2(l_lo * alpha, l_hi * alpha);
+      }
+      const float nmc = -m_ref * c;
+      const uint64_t nmc2 = pack_f32x2(nmc, nmc);
+      uint8_t* p_row = p_row0 + (U & 1) * P_BYTES;
+      if constexpr (kPolyPairs == 0) {
+        // Staged so that no instruction waits on its predecessor: (A) 32 independent packed scales, (B) 64 MUFU.EX2
+        // back to back (the XU pipe, 8 cycles per warp instruction, is the only limiter of this stage and the other
+        // softmax warp of the sub-partition fills the issue slots), (C) row sums on 4 chains + bf16 packing + stores.
+        uint64_t x2[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t)
+          x2[t] = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), c2, nmc2);
+        float pe[64];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float x0, x1;
+          unpack_f32x2(x2[t], x0, x1);
+          pe[2 * t] = ex2_approx(x0);
+          pe[2 * t + 1] = ex2_approx(x1);
+        }
+        uint64_t la = lsum2, lb = lsum2b, lc = pack_f32x2(0.f, 0.f), ld = pack_f32x2(0.f, 0.f);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int t = c8 * 4 + t4;
+            const uint64_t p2 = pack_f32x2(pe[2 * t], pe[2 * t + 1]);
+            if (t4 == 0) la = add_f32x2(la, p2);
+            else if (t4 == 1) lb = add_f32x2(lb, p2);
+            else if (t4 == 2) lc = add_f32x2(lc, p2);
+            else ld = add_f32x2(ld, p2);
+            pk[t4] = pack_bf16x2(pe[2 * t], pe[2 * t + 1]);
+          }
+          *reinterpret_cast<uint4*>(p_row + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        lsum2 = add_f32x2(la, lc);
+        lsum2b = add_f32x2(lb, ld);
+      } else {
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {   // 8 chunks of 8 keys = 16 bytes of bf16
+        uint32_t pk[4];
+#pragma unroll
+        for (int t4 = 0; t4 < 4; ++t4) {
+          const int t = c8 * 4 + t4;     // column pair index
+          const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), c2, nmc2);
+          uint64_t p2;
+          if ((t & 7) < kPolyPairs) {
+            float x0, x1;
+            unpack_f32x2(x2, x0, x1);
+            x0 = fmaxf(x0, -126.0f);
+            x1 = fmaxf(x1, -126.0f);
+            const uint64_t xc = pack_f32x2(x0, x1);
+            const uint64_t xi = add_f32x2(xc, pack_f32x2(12582912.0f, 12582912.0f));
+            const uint64_t xr = add_f32x2(xi, pack_f32x2(-12582912.0f, -12582912.0f));
+            const uint64_t f = fma_f32x2(xr, pack_f32x2(-1.0f, -1.0f), xc);
+            uint64_t q = fma_f32x2(f, pack_f32x2(0.05550411f, 0.05550411f), pack_f32x2(0.24022651f, 0.24022651f));
+            q = fma_f32x2(q, f, pack_f32x2(0.69314718f, 0.69314718f));
+            q = fma_f32x2(q, f, pack_f32x2(1.0f, 1.0f));
+            float q0_, q1_, i0, i1;
+            unpack_f32x2(q, q0_, q1_);
+            unpack_f32x2(xi, i0, i1);
+            q0_ = __uint_as_float(__float_as_uint(q0_) + (__float_as_uint(i0) << 23));
+            q1_ = __uint_as_float(__float_as_uint(q1_) + (__float_as_uint(i1) << 23));
+            p2 = pack_f32x2(q0_, q1_);
+            pk[t4] = pack_bf16x2(q0_, q1_);
+          } else {
+            float x0, x1;
+            unpack_f32x2(x2, x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            p2 = pack_f32x2(p0, p1);
+            pk[t4] = pack_bf16x2(p0, p1);
+          }
+          if (t4 & 1) lsum2b = add_f32x2(lsum2b, p2);
+          else lsum2 = add_f32x2(lsum2, p2);
+        }
+        *reinterpret_cast<uint4*>(p_row + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[i * 2 + (U & 1)]);
+    };
+
+    __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)row * p.o_ls + head * D;
+    int U = 0;
+    for (int si = 0; si < p.n_sets; ++si) {
+      const int kv_len = p.kv_len[si];
+      lsum2 = pack_f32x2(0.f, 0.f);
+      lsum2b = pack_f32x2(0.f, 0.f);
+      if (p.windowed[si]) {
+        step(U, 0, kv_len, std::integral_constant<int, 2>{});
+        ++U;
+      } else {
+        const int ns = (kv_len + SUB - 1) / SUB;
+        for (int u = 0; u < ns - 1; ++u, ++U) step(U, u, kv_len, std::integral_constant<int, 0>{});
+        if (kv_len % SUB) step(U, ns - 1, kv_len, std::integral_constant<int, 1>{});
+        else step(U, ns - 1, kv_len, std::integral_constant<int, 0>{});
+        ++U;
+      }
+      // ---- epilogue of the set: O_i / l -> bf16 -> (+=) global
+      mbar_wait(&o_final[i], si & 1, 0x9500 | i);
+      tc_fence_after();
+      float l_lo, l_hi;
+      lsum2 = add_f32x2(lsum2, lsum2b);
+      unpack_f32x2(lsum2, l_lo, l_hi);
+      const float inv_l = 1.0f / (l_lo + l_hi);
+      const bool acc = p.accumulate || si > 0;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t o[32];
+        tmem_ld_x32(tO + cc * 32, o);
+        tmem_ld_wait();
+        if (cc == 3) {   // all of O_i is in registers: the next set's first P V may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_free[i]);
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int v8 = 0; v8 < 4; ++v8) {
+            float y[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(o[v8 * 8 + t]) * inv_l;
+            uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + v8 * 8);
+            if (acc) {
+              uint4 old = *dst;
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float2 f = __bfloat1622float2(h[t]);
+                y[2 * t] = f.x + bf16_round(y[2 * t]);
+                y[2 * t + 1] = f.y + bf16_round(y[2 * t + 1]);
+              }
+            }
+            uint4 uu;
+            uu.x = pack_bf16x2(y[0], y[1]);
+            uu.y = pack_bf16x2(y[2], y[3]);
+            uu.z = pack_bf16x2(y[4], y[5]);
+            uu.w = pack_bf16x2(y[6], y[7]);
+            *dst = uu;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace attnx
+}  // namespace sa
+
+extern "C" int sa_cross_attn3_d128(const sa_cross_attn_args* a, sa_stream_t stream_) {
+  using namespace sa;
+  using namespace sa::attnx;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->q || !a->out || a->n_sets < 1 || a->n_sets > MAX_SETS || a->batch <= 0 || a->heads <= 0 || a->q_len <= 0) {
+    set_error("sa_cross_attn3_d128: bad argument");
+    return SA_ERR_BAD_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(a->q) & 15) != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) != 0) {
+    set_error("sa_cross_attn3_d128: q / out must be 16-byte aligned");
+    return SA_ERR_BAD_ARG;
+  }
+  Params p;
+  p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.q_bs = a->q_bs; p.q_ls = a->q_ls; p.o_bs = a->o_bs; p.o_ls = a->o_ls;
+  p.q_len = a->q_len;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.accumulate = a->accumulate;
+  p.n_sets = a->n_sets;
+  p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1 << 30;
+  p.tok_offset = a->tok_offset;
+  CUtensorMap tk[MAX_SETS], tv[MAX_SETS];
+  for (int s = 0; s < MAX_SETS; ++s) {
+    const int ss = s < a->n_sets ? s : 0;   // unused slots repeat set 0 (never dereferenced)
+    const sa_cross_attn_set* cs = &a->set[ss];
+    if (!cs->k || !cs->v || cs->kv_len <= 0 || cs->kv_total < cs->kv_len) { set_error("sa_cross_attn3_d128: bad key set %d", ss); return SA_ERR_BAD_ARG; }
+    if (cs->windowed) {
+      // the 256 rows of a CTA touch at most 255 / rows_per_group + 2 consecutive windows; all their keys share one step
+      const int span = 255 / p.rows_per_group + 2;
+      if (a->rows_per_group <= 0 || span * cs->kv_len > SUB) {
+        set_error("sa_cross_attn3_d128: windowed set needs (255 / rows_per_group + 2) * kv_len <= %d", SUB);
+        return SA_ERR_UNSUPPORTED;
+      }
+    }
+    p.kv_len[s] = cs->kv_len;
+    p.windowed[s] = cs->windowed;
+    auto mk = [&](CUtensorMap* m, const void* base, long long ls, long long bs) {
+      uint64_t dims[4] = {(uint64_t)D, (uint64_t)cs->kv_total, (uint64_t)a->heads, (uint64_t)a->batch};
+      uint64_t strides[3] = {(uint64_t)ls * 2, (uint64_t)D * 2, (uint64_t)bs * 2};
+      uint32_t box[4] = {64, SUB, 1, 1};
+      return make_tmap_bf16(m, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    };
+    int rc;
+    if ((rc = mk(&tk[s], cs->k, cs->k_ls, cs->k_bs))) return rc;
+    if ((rc = mk(&tv[s], cs->v, cs->v_ls, cs->v_bs))) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cross_attn_kernel)");
+    attr_set = true;
+  }
+  dim3 grid((a->q_len + 2 * BQ - 1) / (2 * BQ), a->heads, a->batch);
+  cross_attn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk[0], tv[0], tk[1], tv[1], tk[2], tv[2], p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "cross_attn_kernel launch");
+  return SA_OK;
+}

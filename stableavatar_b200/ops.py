@@ -381,3 +381,41 @@ def ipc_open(handle):
 
 def ipc_close(base):
     L.check(L.lib().sa_ipc_close(C.c_void_p(base)), "sa_ipc_close")
+
+
+# ---------------------------------------------------------------------------------------------- fused cross-attention
+class CrossSet(C.Structure):
+    _fields_ = [("k", C.c_void_p), ("v", C.c_void_p), ("k_bs", C.c_int64), ("k_ls", C.c_int64), ("v_bs", C.c_int64),
+                ("v_ls", C.c_int64), ("kv_len", C.c_int32), ("kv_total", C.c_int32), ("windowed", C.c_int32)]
+
+
+class CrossArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("out", C.c_void_p), ("q_bs", C.c_int64), ("q_ls", C.c_int64), ("o_bs", C.c_int64),
+                ("o_ls", C.c_int64), ("batch", C.c_int32), ("heads", C.c_int32), ("q_len", C.c_int32), ("n_sets", C.c_int32),
+                ("scale", C.c_float), ("accumulate", C.c_int32), ("rows_per_group", C.c_int32), ("tok_offset", C.c_int32),
+                ("set", CrossSet * 3)]
+
+
+def cross_attn3(q, sets, out=None, accumulate=False, rows_per_group=0, tok_offset=0, scale=None):
+    """out (+)= sum_s softmax(q K_s^T * scale) V_s in one launch — sa_cross_attn3_d128. q/out [B, Lq, H, 128] bf16 views;
+    sets: up to three (k, v, window) with k, v [B, Lk, H, 128] views; window = 0 for a plain set, else the keys are
+    Lk / window consecutive windows and row r attends to window (tok_offset + r) // rows_per_group."""
+    _need_cuda(q)
+    B, Lq, H, D = q.shape
+    assert D == 128 and 1 <= len(sets) <= 3
+    if out is None:
+        assert not accumulate
+        out = torch.empty(q.shape, device=q.device, dtype=torch.bfloat16)
+    for t in (q, out):
+        assert t.dtype == torch.bfloat16 and t.stride(3) == 1 and t.stride(2) == D
+    a = CrossArgs(q=q.data_ptr(), out=out.data_ptr(), q_bs=q.stride(0), q_ls=q.stride(1), o_bs=out.stride(0), o_ls=out.stride(1),
+                  batch=B, heads=H, q_len=Lq, n_sets=len(sets), scale=scale if scale is not None else D ** -0.5,
+                  accumulate=int(accumulate), rows_per_group=rows_per_group, tok_offset=tok_offset)
+    for i, (k, v, window) in enumerate(sets):
+        assert k.shape == v.shape and k.shape[0] == B and k.shape[2] == H and k.shape[3] == D
+        for t in (k, v):
+            assert t.dtype == torch.bfloat16 and t.stride(3) == 1 and t.stride(2) == D
+        a.set[i] = CrossSet(k=k.data_ptr(), v=v.data_ptr(), k_bs=k.stride(0), k_ls=k.stride(1), v_bs=v.stride(0), v_ls=v.stride(1),
+                            kv_len=window if window else k.shape[1], kv_total=k.shape[1], windowed=int(bool(window)))
+    L.check(L.lib().sa_cross_attn3_d128(C.byref(a), L.stream_ptr()), "sa_cross_attn3_d128")
+    return out

@@ -14,6 +14,7 @@ there is no CPU or eager fallback.
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -389,7 +390,8 @@ class WanTransformer3DFantasyModel(nn.Module):
         e_all = ops.add_bcast(p["mods"], e0)                                       # [layers, B, 6C]
         freqs = self._freqs_table(dev)
         state = dict(B=B, L=L, C=C, nh=nh, G=G, grid=(F, Hp, Wp), freqs=freqs, ctx_txt=ctx_txt, ctx_img=ctx_img,
-                     vc=vc.reshape(B, -1, C).contiguous(), vc_grouped=vc.dim() == 4)
+                     vc=vc.reshape(B, -1, C).contiguous(), vc_grouped=vc.dim() == 4,
+                     fused_cross=os.environ.get("SA_CROSS_FUSED", "1") != "0")
 
         if P > 1:
             from . import sequence_parallel as sp
@@ -486,13 +488,24 @@ class WanTransformer3DFantasyModel(nn.Module):
         q4 = q.view(B, Ll, nh, 128)
         kv5 = kv.view(B, -1, 2, nh, 128)
         kvi5 = kvi.view(B, -1, 2, nh, 128)
-        a = ops.flash_attn(q4, kv5[:, :, 0], kv5[:, :, 1])
-        ops.flash_attn(q4, kvi5[:, :, 0], kvi5[:, :, 1], out=a, accumulate=True)
-        if st["vc_grouped"]:
-            self._audio_attention(q, kvv, a, st, Ll)
+        kvv5 = kvv.view(B, -1, 2, nh, 128)
+        window, gs = 0, 0
+        if st["vc_grouped"]:                               # token group g <-> audio window g (1B.py:575-586)
+            window, gs = kvv5.shape[1] // st["G"], st["L"] // st["G"]
+        fused = st["fused_cross"] and (not window or (st["L"] % st["G"] == 0 and (255 // gs + 2) * window <= 64))
+        if fused:
+            # one launch: q read once, the three key sets walked back to back (csrc/attn_cross_tcgen05.cu)
+            with ops.timed("cross_attn"):
+                a = ops.cross_attn3(q4, [(kv5[:, :, 0], kv5[:, :, 1], 0), (kvi5[:, :, 0], kvi5[:, :, 1], 0),
+                                         (kvv5[:, :, 0], kvv5[:, :, 1], window)], rows_per_group=gs, tok_offset=st.get("tok0", 0))
         else:
-            kvv5 = kvv.view(B, -1, 2, nh, 128)
-            ops.flash_attn(q4, kvv5[:, :, 0], kvv5[:, :, 1], out=a, accumulate=True)
+            with ops.timed("cross_attn"):
+                a = ops.flash_attn(q4, kv5[:, :, 0], kv5[:, :, 1])
+                ops.flash_attn(q4, kvi5[:, :, 0], kvi5[:, :, 1], out=a, accumulate=True)
+                if st["vc_grouped"]:
+                    self._audio_attention(q, kvv, a, st, Ll)
+                else:
+                    ops.flash_attn(q4, kvv5[:, :, 0], kvv5[:, :, 1], out=a, accumulate=True)
         ops.gemm(a.view(B * Ll, C), ca.o.weight, ca.o.bias, res=h, out=h)
 
         # ---- FFN (1B.py:687-691)

@@ -170,3 +170,45 @@ def test_config1_grid_480x832x5_vs_oracle():
                             inp["seq_len"], r(inp["clip_fea"]), r(inp["y"]), r(inp["vocal_embeddings"]), 5)
     assert out.shape == (3, 16, 2, 60, 104)
     assert rel(out.float().cpu(), ref) < 2e-2
+
+
+def _cross_inputs(B, Lq, Hh, G, A, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    mk = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()  # noqa: E731
+    return mk(B, Lq, Hh, 128), (mk(B, 512, Hh, 128), mk(B, 512, Hh, 128)), (mk(B, 257, Hh, 128), mk(B, 257, Hh, 128)), \
+        (mk(B, G * A, Hh, 128), mk(B, G * A, Hh, 128))
+
+
+@pytest.mark.parametrize("Lq,G,tok_offset,L_total", [(3120, 2, 0, 3120),      # config-1 grid: 2 windows of 1560 rows
+                                                     (1700, 3, 1000, 4680),   # token shard [1000, 2700) of 3 x 1560
+                                                     (520, 4, 0, 520)])       # 130-row groups: 4 windows inside one CTA
+def test_fused_cross_attention_equals_three_launches(ops, Lq, G, tok_offset, L_total):
+    """sa_cross_attn3_d128 (text + image + windowed audio in one launch) against three sa_flash_attn_d128 launches with
+    accumulate (bit-identical by construction) and against fp32 torch SDPA per set."""
+    B, Hh, A = 2, 3, 15
+    gs = L_total // G
+    q, (kt, vt), (ki, vi), (ka, va) = _cross_inputs(B, Lq, Hh, G, A, 11)
+    got = ops.cross_attn3(q, [(kt, vt, 0), (ki, vi, 0), (ka, va, A)], rows_per_group=gs, tok_offset=tok_offset)
+    want = ops.flash_attn(q, kt, vt)
+    ops.flash_attn(q, ki, vi, out=want, accumulate=True)
+    ref = sdpa(q, kt, vt) + sdpa(q, ki, vi)
+    for g in range((tok_offset) // gs, (tok_offset + Lq - 1) // gs + 1):
+        lo, hi = max(g * gs, tok_offset) - tok_offset, min((g + 1) * gs, tok_offset + Lq) - tok_offset
+        ops.flash_attn(q[:, lo:hi], ka[:, g * A:(g + 1) * A], va[:, g * A:(g + 1) * A], out=want[:, lo:hi], accumulate=True)
+        ref[:, lo:hi] += sdpa(q[:, lo:hi], ka[:, g * A:(g + 1) * A], va[:, g * A:(g + 1) * A])
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    assert rel(got.float(), ref) < 6e-3
+
+
+def test_fused_cross_attention_plain_sets_and_accumulate(ops):
+    """Clip-level audio (no windows): three plain sets; accumulate adds onto an existing output."""
+    q, (kt, vt), (ki, vi), (ka, va) = _cross_inputs(1, 300, 2, 3, 15, 12)
+    base = torch.randn(q.shape, device="cuda").bfloat16()
+    got = ops.cross_attn3(q, [(kt, vt, 0), (ki, vi, 0), (ka, va, 0)], out=base.clone(), accumulate=True)
+    want = base.clone()
+    for k, v in ((kt, vt), (ki, vi), (ka, va)):
+        ops.flash_attn(q, k, v, out=want, accumulate=True)
+    assert torch.equal(got, want)
+    one = ops.cross_attn3(q, [(ki, vi, 0)])
+    assert torch.equal(one, ops.flash_attn(q, ki, vi))
