@@ -82,7 +82,7 @@ int sa_flash_attn_d128(const sa_attn_args* args, sa_stream_t stream);
  * q loaded once. q/out: bf16 [batch, q_len, heads, 128] views as in sa_attn_args. A set is [batch, kv_total, heads, 128]
  * (strides k_bs/k_ls, v_bs/v_ls). windowed = 0: all kv_len = kv_total keys. windowed = 1 (audio, 1B.py:575-586): the keys
  * are kv_total / kv_len consecutive windows of kv_len keys and query row r attends only to window
- * (tok_offset + r) / rows_per_group; requires (255 / rows_per_group + 2) * kv_len <= 64. */
+ * (tok_offset + r) / rows_per_group; requires (127 / rows_per_group + 2) * kv_len <= 64. */
 typedef struct {
   const void* k;
   const void* v;

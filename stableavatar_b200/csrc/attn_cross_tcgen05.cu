@@ -3,11 +3,12 @@
 // WanI2VTalkingCrossAttention (wan/models/wan_fantasy_transformer3d_1B.py:534-605) sums three softmax attentions that
 // share the query: text (512 keys), CLIP image (257 keys) and audio (15 keys of the latent frame's audio window, paired
 // with the token group by q.view(b * G, -1, n, d), :575-586). As three launches of the self-attention kernel each one
-// re-reads Q (302 MB at B = 3) and read-modify-writes O; here a CTA loads its two 128-row Q tiles into TMEM once and
-// walks the key sets back to back through the same decoupled pipeline as attn_v8_tcgen05.cu (global step counter, so
-// all mbarrier phases simply keep running), finishing each set with the usual O / l epilogue that adds into the
-// output rows it wrote a few microseconds earlier (L2 hits). Per-set rounding and order (text, image, audio; every
-// partial result rounded to bf16 before the bf16 add) are those of the three-launch path, so results are bit-identical.
+// re-reads Q (302 MB at B = 3) and read-modify-writes O, and — with only 8 + 5 + 1 key steps — every CTA spends most of
+// its life filling and draining its pipeline. Here a CTA owns ONE 128-row Q tile, loads it into TMEM once and walks the
+// key sets back to back through the decoupled pipeline of attn_v8_tcgen05.cu (global step counter, so all mbarrier
+// phases simply keep running) with ONE TMEM ACCUMULATOR PER SET (Q 64 + S 64 + 3 x 128 columns = 512): nothing drains
+// at a set boundary, and a single epilogue forms bf16(O_0 / l_0) + bf16(O_1 / l_1) + bf16(O_2 / l_2) in the rounding
+// order of the three-launch path (text, image, audio; bf16 adds), so results are bit-identical and O is written once.
 //
 // The audio set is one 64-key step: the keys of the (at most 64 / A) consecutive windows that the CTA's 256 rows can
 // touch are loaded together and every row masks the step down to its own window [ (g - g0) A, (g - g0) A + A ), with
@@ -29,9 +30,9 @@ constexpr int KV_PANEL = SUB * 128;          // 64 rows x 128 B = 8 KB
 constexpr int KV_TILE = 2 * KV_PANEL;        // [64 keys x 128 d] = 16 KB
 constexpr int STAGE_BYTES = 2 * KV_TILE;     // K + V
 constexpr int P_BYTES = BQ * 128;            // [128 rows x 64 keys] bf16 = 16 KB
-constexpr int NUM_THREADS = 352;   // 8 softmax warps, TMA producer, one MMA-issuing warp per Q tile
+constexpr int NUM_THREADS = 192;   // 4 softmax warps (one Q tile), TMA producer, MMA issuer
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * P_BYTES + 256 + 1024;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * P_BYTES + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;
 
 constexpr int MAX_SETS = 3;
@@ -56,25 +57,21 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sKV = smem;                                   // [STAGES][K tile | V tile]
-  uint8_t* sP = smem + STAGES * STAGE_BYTES;             // [2 q tiles][2 buffers][P_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * P_BYTES);
+  uint8_t* sP = smem + STAGES * STAGE_BYTES;             // [2 buffers][P_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
   uint64_t* kv_full = bars;                 // [STAGES]
   uint64_t* kv_empty = bars + STAGES;       // [STAGES]
-  uint64_t* s_full = bars + 2 * STAGES;     // [2]  S_i(u) complete in TMEM
-  uint64_t* s_cons = s_full + 2;            // [2]  softmax i has S_i(u) in registers
-  uint64_t* p_full = s_cons + 2;            // [2 tiles][2 P buffers]  P_i(u) in shared memory (and O_i rescaled if needed).
-                                            // One barrier per P buffer: a softmax warpgroup may finish steps u and u+1
-                                            // before the MMA warp (held up by the other tile) consumes P_i(u); with a
-                                            // single barrier those two completions would alias in the phase parity.
-  uint64_t* pv_done = p_full + 4;           // [2]  one completion per PV_i(u)
-  uint64_t* o_final = pv_done + 2;          // [2]
-  uint64_t* q_ready = o_final + 2;          // [1]  Q tiles stored in TMEM
-  uint64_t* o_free = q_ready + 1;           // [2]  the epilogue of a set has read O_i: the next set may overwrite it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* s_full = bars + 2 * STAGES;     // [1]  S(U) complete in TMEM
+  uint64_t* s_cons = s_full + 1;            // [1]  the softmax warps have S(U) in registers
+  uint64_t* p_full = s_cons + 1;            // [2 P buffers]  P(U) in shared memory (and O rescaled if needed)
+  uint64_t* pv_done = p_full + 2;           // [1]  one completion per P(U) V
+  uint64_t* o_final = pv_done + 1;          // [1]  every accumulator is complete
+  uint64_t* q_ready = o_final + 1;          // [1]  Q tile stored in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * BQ);
+  const int q0 = blockIdx.x * BQ;
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   auto n_sub_of = [&](int si) { return p.windowed[si] ? 1 : (p.kv_len[si] + SUB - 1) / SUB; };
@@ -82,25 +79,22 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
   for (int si = 0; si < p.n_sets; ++si) n_total += n_sub_of(si);
   const int g0 = (p.tok_offset + q0) / p.rows_per_group;   // first window any row of this CTA can belong to
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tk0);
     tma_prefetch_desc(&tv0);
   }
-  if (warp == 9) {
+  if (warp == 5) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&kv_full[s], 1);
-        mbar_init(&kv_empty[s], 2);   // one tcgen05.commit per MMA warp
+        mbar_init(&kv_empty[s], 1);
       }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&s_full[i], 1);
-        mbar_init(&s_cons[i], 4);
-        mbar_init(&pv_done[i], 1);
-        mbar_init(&o_final[i], 1);
-        mbar_init(&o_free[i], 4);
-      }
-      for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
-      mbar_init(q_ready, 8);
+      mbar_init(s_full, 1);
+      mbar_init(s_cons, 4);
+      mbar_init(pv_done, 1);
+      mbar_init(o_final, 1);
+      for (int i = 0; i < 2; ++i) mbar_init(&p_full[i], 4);
+      mbar_init(q_ready, 4);
       fence_barrier_init();
     }
     __syncwarp();
@@ -112,7 +106,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 4) {
     // ------------------------------------------------------------ TMA producer: {K, V} 64-key tiles
     if (elect_one()) {  // elect.sync: single active lane is known to ptxas -> no R2UR waterfall per UTCHMMA / UTMALDG
       int U = 0;
@@ -134,12 +128,9 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
         }
       }
     }
-  } else if (warp == 9 || warp == 10) {
-    // ------------------------------------------------------------ MMA issuers: one warp per Q tile, so that the next
-    // score tile of a Q tile is issued the moment its softmax warpgroup has consumed the current one, whatever the
-    // other tile is doing (a single issuer serving both tiles in a fixed order parks on the other tile's P).
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer. TMEM columns: Q 0-63, S 64-127, O_set 128 + 128 set.
     if (elect_one()) {
-      const int i = warp - 9;
       const uint32_t idesc_qk = umma_idesc_bf16(BQ, SUB, 0, 0);  // A = Q (TMEM), B = 64 keys of K (K-major)
       const uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);    // A = P (smem, K-major), B = V (MN-major)
       auto issue_S = [&](int u) {
@@ -147,20 +138,19 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t off = (k >> 2) * KV_PANEL + (k & 3) * 32;
-          umma_ts(tmem_base + 128 + i * SUB, tmem_base + i * 64 + k * 8, umma_smem_desc(ka + off, 16, 1024, kSwz128),
-                  idesc_qk, k != 0);
+          umma_ts(tmem_base + 64, tmem_base + k * 8, umma_smem_desc(ka + off, 16, 1024, kSwz128), idesc_qk, k != 0);
         }
-        umma_commit(&s_full[i]);
+        umma_commit(s_full);
       };
-      auto issue_PV = [&](int u, bool first) {
+      auto issue_PV = [&](int u, int si, bool first) {
         const uint32_t va = smem_u32(sKV + (u % STAGES) * STAGE_BYTES + KV_TILE);
-        const uint32_t pa = smem_u32(sP + (i * 2 + (u & 1)) * P_BYTES);
+        const uint32_t pa = smem_u32(sP + (u & 1) * P_BYTES);
 #pragma unroll
         for (int k = 0; k < SUB / 16; ++k) {
-          umma_ss(tmem_base + 256 + i * 128, umma_smem_desc(pa + k * 32, 16, 1024, kSwz128),
+          umma_ss(tmem_base + 128 + si * 128, umma_smem_desc(pa + k * 32, 16, 1024, kSwz128),
                   umma_smem_desc(va + k * 2048, KV_PANEL, 1024, kSwz128), idesc_pv, (!first || k != 0) ? 1u : 0u);
         }
-        umma_commit(&pv_done[i]);
+        umma_commit(pv_done);
       };
       mbar_wait(q_ready, 0, 0x9300);
       mbar_wait(&kv_full[0], 0, 0x9310);
@@ -172,31 +162,29 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
         for (int u = 0; u < ns; ++u, ++U) {
           if (U + 1 < n_total) {
             mbar_wait(&kv_full[(U + 1) % STAGES], ((U + 1) / STAGES) & 1, 0x9320 | ((U + 1) % STAGES));
-            mbar_wait(&s_cons[i], U & 1, 0x9330 | i);   // S_i(U) is in the softmax registers: its columns are free
+            mbar_wait(s_cons, U & 1, 0x9330);   // S(U) is in the softmax registers: its columns are free
             tc_fence_after();
             issue_S(U + 1);
           }
-          mbar_wait(&p_full[i * 2 + (U & 1)], (U >> 1) & 1, 0x9340 | (i * 2 + (U & 1)));
-          if (u == 0 && si > 0) mbar_wait(&o_free[i], (si - 1) & 1, 0x9350 | i);   // previous set's O has been read out
+          mbar_wait(&p_full[U & 1], (U >> 1) & 1, 0x9340 | (U & 1));
           tc_fence_after();
-          issue_PV(U, u == 0);
-          if (u == ns - 1) umma_commit(&o_final[i]);
-          umma_commit(&kv_empty[U % STAGES]);   // this tile is done with K(U), V(U)
+          issue_PV(U, si, u == 0);
+          if (U == n_total - 1) umma_commit(o_final);
+          umma_commit(&kv_empty[U % STAGES]);   // done with K(U), V(U)
         }
       }
     }
   } else {
     // ------------------------------------------------------------ softmax warpgroups (one thread per query row)
-    const int i = warp >> 2;  // Q tile
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row inside the tile
     const uint32_t lane_sel = uint32_t(quarter * 32) << 16;
-    const uint32_t tQ = tmem_base + lane_sel + i * 64;
-    const uint32_t tS = tmem_base + lane_sel + 128 + i * SUB;
-    const uint32_t tO = tmem_base + lane_sel + 256 + i * 128;
-    const int row = q0 + i * BQ + r;
+    const uint32_t tQ = tmem_base + lane_sel;
+    const uint32_t tS = tmem_base + lane_sel + 64;
+    const uint32_t tO0 = tmem_base + lane_sel + 128;
+    const int row = q0 + r;
     const bool row_ok = row < p.q_len;
-    uint8_t* p_row0 = sP + i * 2 * P_BYTES + r * 128;
+    uint8_t* p_row0 = sP + r * 128;
 
     // ---- Q row -> TMEM (A operand layout: lane = row, column c holds elements 2c, 2c+1)
     {
@@ -223,9 +211,9 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
     uint64_t lsum2 = pack_f32x2(0.f, 0.f), lsum2b = pack_f32x2(0.f, 0.f);  // two independent row-sum chains
 
     // U: global step (barrier phases, P buffer), u: step inside the current set, MASK: 0 none, 1 ragged tail, 2 window
-    auto step = [&](int U, int u, int kv_len, auto mask_tag) {
+    auto step = [&](int U, int u, int kv_len, uint32_t tO, auto mask_tag) {
       constexpr int MASK = decltype(mask_tag)::value;
-      mbar_wait(&s_full[i], U & 1, 0x9400 | i);
+      mbar_wait(s_full, U & 1, 0x9400);
       tc_fence_after();
       uint32_t s[SUB];
       {
@@ -237,7 +225,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_cons[i]);   // the MMA warp may overwrite S_i with the next step's scores
+      if (lane == 0) mbar_arrive(s_cons);   // the MMA warp may overwrite S with the next step's scores
       if constexpr (MASK == 1) {
         const int valid = kv_len - u * SUB;
 #pragma unroll
@@ -273,7 +261,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
       // The P panel is double-buffered: P_i(u-2) V completed before S_i(u) did (issue order), so buffer u&1 is free.
       if (__any_sync(0xffffffffu, need)) {
         // P_i(u-1) V may still be accumulating into O_i: wait for it before rescaling (u >= 1 here).
-        mbar_wait(&pv_done[i], (U - 1) & 1, 0x9450 | i);
+        mbar_wait(pv_done, (U - 1) & 1, 0x9450);
         tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
@@ -372,67 +360,80 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i * 2 + (U & 1)]);
+      if (lane == 0) mbar_arrive(&p_full[U & 1]);
     };
 
-    __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)row * p.o_ls + head * D;
+    float inv_l[MAX_SETS] = {0.f, 0.f, 0.f};
     int U = 0;
-    for (int si = 0; si < p.n_sets; ++si) {
-      const int kv_len = p.kv_len[si];
-      lsum2 = pack_f32x2(0.f, 0.f);
-      lsum2b = pack_f32x2(0.f, 0.f);
-      if (p.windowed[si]) {
-        step(U, 0, kv_len, std::integral_constant<int, 2>{});
-        ++U;
-      } else {
-        const int ns = (kv_len + SUB - 1) / SUB;
-        for (int u = 0; u < ns - 1; ++u, ++U) step(U, u, kv_len, std::integral_constant<int, 0>{});
-        if (kv_len % SUB) step(U, ns - 1, kv_len, std::integral_constant<int, 1>{});
-        else step(U, ns - 1, kv_len, std::integral_constant<int, 0>{});
-        ++U;
-      }
-      // ---- epilogue of the set: O_i / l -> bf16 -> (+=) global
-      mbar_wait(&o_final[i], si & 1, 0x9500 | i);
-      tc_fence_after();
-      float l_lo, l_hi;
-      lsum2 = add_f32x2(lsum2, lsum2b);
-      unpack_f32x2(lsum2, l_lo, l_hi);
-      const float inv_l = 1.0f / (l_lo + l_hi);
-      const bool acc = p.accumulate || si > 0;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t o[32];
-        tmem_ld_x32(tO + cc * 32, o);
-        tmem_ld_wait();
-        if (cc == 3) {   // all of O_i is in registers: the next set's first P V may overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&o_free[i]);
+#pragma unroll
+    for (int si = 0; si < MAX_SETS; ++si) {
+      if (si < p.n_sets) {
+        const int kv_len = p.kv_len[si];
+        const uint32_t tO = tO0 + si * 128;
+        lsum2 = pack_f32x2(0.f, 0.f);
+        lsum2b = pack_f32x2(0.f, 0.f);
+        if (p.windowed[si]) {
+          step(U, 0, kv_len, tO, std::integral_constant<int, 2>{});
+          ++U;
+        } else {
+          const int ns = (kv_len + SUB - 1) / SUB;
+          for (int u = 0; u < ns - 1; ++u, ++U) step(U, u, kv_len, tO, std::integral_constant<int, 0>{});
+          if (kv_len % SUB) step(U, ns - 1, kv_len, tO, std::integral_constant<int, 1>{});
+          else step(U, ns - 1, kv_len, tO, std::integral_constant<int, 0>{});
+          ++U;
         }
-        if (row_ok) {
+        float l_lo, l_hi;
+        lsum2 = add_f32x2(lsum2, lsum2b);
+        unpack_f32x2(lsum2, l_lo, l_hi);
+        inv_l[si] = 1.0f / (l_lo + l_hi);
+      }
+    }
+
+    // ---- epilogue: bf16(O_0 / l_0) (+ bf16(O_1 / l_1)) (+ bf16(O_2 / l_2)) in bf16 adds -> global, written once
+    mbar_wait(o_final, 0, 0x9500);
+    tc_fence_after();
+    __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)row * p.o_ls + head * D;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      float y[32];
+      if (p.accumulate && row_ok) {
 #pragma unroll
-          for (int v8 = 0; v8 < 4; ++v8) {
-            float y[8];
+        for (int v8 = 0; v8 < 4; ++v8) {
+          const uint4 old = *reinterpret_cast<const uint4*>(orow + cc * 32 + v8 * 8);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&old);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(o[v8 * 8 + t]) * inv_l;
-            uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + v8 * 8);
-            if (acc) {
-              uint4 old = *dst;
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&old);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                float2 f = __bfloat1622float2(h[t]);
-                y[2 * t] = f.x + bf16_round(y[2 * t]);
-                y[2 * t + 1] = f.y + bf16_round(y[2 * t + 1]);
-              }
-            }
-            uint4 uu;
-            uu.x = pack_bf16x2(y[0], y[1]);
-            uu.y = pack_bf16x2(y[2], y[3]);
-            uu.z = pack_bf16x2(y[4], y[5]);
-            uu.w = pack_bf16x2(y[6], y[7]);
-            *dst = uu;
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __bfloat1622float2(h[t]);
+            y[v8 * 8 + 2 * t] = f.x;
+            y[v8 * 8 + 2 * t + 1] = f.y;
           }
+        }
+      }
+#pragma unroll
+      for (int si = 0; si < MAX_SETS; ++si) {
+        if (si < p.n_sets) {
+          uint32_t o[32];
+          tmem_ld_x32(tO0 + si * 128 + cc * 32, o);
+          tmem_ld_wait();
+          const float il = inv_l[si];
+          if (si == 0 && !p.accumulate) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) y[t] = bf16_round(__uint_as_float(o[t]) * il);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) y[t] = bf16_round(y[t] + bf16_round(__uint_as_float(o[t]) * il));
+          }
+        }
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int v8 = 0; v8 < 4; ++v8) {
+          uint4 uu;
+          uu.x = pack_bf16x2(y[v8 * 8], y[v8 * 8 + 1]);
+          uu.y = pack_bf16x2(y[v8 * 8 + 2], y[v8 * 8 + 3]);
+          uu.z = pack_bf16x2(y[v8 * 8 + 4], y[v8 * 8 + 5]);
+          uu.w = pack_bf16x2(y[v8 * 8 + 6], y[v8 * 8 + 7]);
+          *reinterpret_cast<uint4*>(orow + cc * 32 + v8 * 8) = uu;
         }
       }
     }
@@ -440,7 +441,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -477,10 +478,10 @@ extern "C" int sa_cross_attn3_d128(const sa_cross_attn_args* a, sa_stream_t stre
     const sa_cross_attn_set* cs = &a->set[ss];
     if (!cs->k || !cs->v || cs->kv_len <= 0 || cs->kv_total < cs->kv_len) { set_error("sa_cross_attn3_d128: bad key set %d", ss); return SA_ERR_BAD_ARG; }
     if (cs->windowed) {
-      // the 256 rows of a CTA touch at most 255 / rows_per_group + 2 consecutive windows; all their keys share one step
-      const int span = 255 / p.rows_per_group + 2;
+      // the 128 rows of a CTA touch at most 127 / rows_per_group + 2 consecutive windows; all their keys share one step
+      const int span = 127 / p.rows_per_group + 2;
       if (a->rows_per_group <= 0 || span * cs->kv_len > SUB) {
-        set_error("sa_cross_attn3_d128: windowed set needs (255 / rows_per_group + 2) * kv_len <= %d", SUB);
+        set_error("sa_cross_attn3_d128: windowed set needs (127 / rows_per_group + 2) * kv_len <= %d", SUB);
         return SA_ERR_UNSUPPORTED;
       }
     }
@@ -502,7 +503,7 @@ extern "C" int sa_cross_attn3_d128(const sa_cross_attn_args* a, sa_stream_t stre
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cross_attn_kernel)");
     attr_set = true;
   }
-  dim3 grid((a->q_len + 2 * BQ - 1) / (2 * BQ), a->heads, a->batch);
+  dim3 grid((a->q_len + BQ - 1) / BQ, a->heads, a->batch);
   cross_attn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk[0], tv[0], tk[1], tv[1], tk[2], tv[2], p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "cross_attn_kernel launch");

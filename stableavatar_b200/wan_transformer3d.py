@@ -492,7 +492,7 @@ class WanTransformer3DFantasyModel(nn.Module):
         window, gs = 0, 0
         if st["vc_grouped"]:                               # token group g <-> audio window g (1B.py:575-586)
             window, gs = kvv5.shape[1] // st["G"], st["L"] // st["G"]
-        fused = st["fused_cross"] and (not window or (st["L"] % st["G"] == 0 and (255 // gs + 2) * window <= 64))
+        fused = st["fused_cross"] and (not window or (st["L"] % st["G"] == 0 and (127 // gs + 2) * window <= 64))
         if fused:
             # one launch: q read once, the three key sets walked back to back (csrc/attn_cross_tcgen05.cu)
             with ops.timed("cross_attn"):
