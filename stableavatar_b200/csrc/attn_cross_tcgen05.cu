@@ -3,12 +3,15 @@
 // WanI2VTalkingCrossAttention (wan/models/wan_fantasy_transformer3d_1B.py:534-605) sums three softmax attentions that
 // share the query: text (512 keys), CLIP image (257 keys) and audio (15 keys of the latent frame's audio window, paired
 // with the token group by q.view(b * G, -1, n, d), :575-586). As three launches of the self-attention kernel each one
-// re-reads Q (302 MB at B = 3) and read-modify-writes O, and — with only 8 + 5 + 1 key steps — every CTA spends most of
-// its life filling and draining its pipeline. Here a CTA owns ONE 128-row Q tile, loads it into TMEM once and walks the
-// key sets back to back through the decoupled pipeline of attn_v8_tcgen05.cu (global step counter, so all mbarrier
-// phases simply keep running) with ONE TMEM ACCUMULATOR PER SET (Q 64 + S 64 + 3 x 128 columns = 512): nothing drains
-// at a set boundary, and a single epilogue forms bf16(O_0 / l_0) + bf16(O_1 / l_1) + bf16(O_2 / l_2) in the rounding
-// order of the three-launch path (text, image, audio; bf16 adds), so results are bit-identical and O is written once.
+// re-reads Q (302 MB at B = 3) and read-modify-writes O, and — with only 8 + 5 + 1 key steps — a CTA spends most of its
+// life filling and draining its pipeline (measured: ~1.8 us per 64-key step against 0.52 us per tile-step in
+// self-attention). Here a CTA owns ONE 128-row Q tile, loads it into TMEM once and walks the key sets back to back
+// through the decoupled pipeline of attn_v8_tcgen05.cu (global step counter, so all mbarrier phases simply keep
+// running); each set ends with the usual O / l epilogue that adds into the output row the same thread wrote a few
+// microseconds earlier (L2 hit). The CTA is sized for TWO RESIDENT CTAs PER SM — 256 TMEM columns (Q 64 + S 64 + O 128),
+// 2 K/V stages + the P double buffer = 96 KB, 192 threads — so one CTA's fill / drain / epilogue overlaps the other's
+// steady state. Per-set rounding and order (text, image, audio; every partial result rounded to bf16 before the bf16
+// add) are those of the three-launch path, so results are bit-identical.
 //
 // The audio set is one 64-key step: the keys of the (at most 64 / A) consecutive windows that the CTA's 256 rows can
 // touch are loaded together and every row masks the step down to its own window [ (g - g0) A, (g - g0) A + A ), with
@@ -25,13 +28,13 @@ namespace sa {
 namespace attnx {
 
 constexpr int BQ = 128, SUB = 64, D = 128;
-constexpr int STAGES = 4;
+constexpr int STAGES = 2;           // short key sets: two stages, so that two CTAs fit in one SM's shared memory
 constexpr int KV_PANEL = SUB * 128;          // 64 rows x 128 B = 8 KB
 constexpr int KV_TILE = 2 * KV_PANEL;        // [64 keys x 128 d] = 16 KB
 constexpr int STAGE_BYTES = 2 * KV_TILE;     // K + V
 constexpr int P_BYTES = BQ * 128;            // [128 rows x 64 keys] bf16 = 16 KB
 constexpr int NUM_THREADS = 192;   // 4 softmax warps (one Q tile), TMA producer, MMA issuer
-constexpr int TMEM_COLS = 512;
+constexpr int TMEM_COLS = 256;        // Q 0-63, S 64-127, O 128-255: two CTAs share the SM's 512 columns
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * P_BYTES + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;
 
@@ -49,7 +52,7 @@ struct Params {
   int rows_per_group, tok_offset;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant__ CUtensorMap tv0,
                   const __grid_constant__ CUtensorMap tk1, const __grid_constant__ CUtensorMap tv1,
                   const __grid_constant__ CUtensorMap tk2, const __grid_constant__ CUtensorMap tv2, const Params p) {
@@ -67,7 +70,8 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
   uint64_t* pv_done = p_full + 2;           // [1]  one completion per P(U) V
   uint64_t* o_final = pv_done + 1;          // [1]  every accumulator is complete
   uint64_t* q_ready = o_final + 1;          // [1]  Q tile stored in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
+  uint64_t* o_free = q_ready + 1;           // [1]  the epilogue of a set has read O: the next set may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,6 +97,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
       mbar_init(s_cons, 4);
       mbar_init(pv_done, 1);
       mbar_init(o_final, 1);
+      mbar_init(o_free, 4);
       for (int i = 0; i < 2; ++i) mbar_init(&p_full[i], 4);
       mbar_init(q_ready, 4);
       fence_barrier_init();
@@ -129,7 +134,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------ MMA issuer. TMEM columns: Q 0-63, S 64-127, O_set 128 + 128 set.
+    // ------------------------------------------------------------ MMA issuer. TMEM columns: Q 0-63, S 64-127, O 128-255.
     if (elect_one()) {
       const uint32_t idesc_qk = umma_idesc_bf16(BQ, SUB, 0, 0);  // A = Q (TMEM), B = 64 keys of K (K-major)
       const uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);    // A = P (smem, K-major), B = V (MN-major)
@@ -142,12 +147,12 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
         }
         umma_commit(s_full);
       };
-      auto issue_PV = [&](int u, int si, bool first) {
+      auto issue_PV = [&](int u, bool first) {
         const uint32_t va = smem_u32(sKV + (u % STAGES) * STAGE_BYTES + KV_TILE);
         const uint32_t pa = smem_u32(sP + (u & 1) * P_BYTES);
 #pragma unroll
         for (int k = 0; k < SUB / 16; ++k) {
-          umma_ss(tmem_base + 128 + si * 128, umma_smem_desc(pa + k * 32, 16, 1024, kSwz128),
+          umma_ss(tmem_base + 128, umma_smem_desc(pa + k * 32, 16, 1024, kSwz128),
                   umma_smem_desc(va + k * 2048, KV_PANEL, 1024, kSwz128), idesc_pv, (!first || k != 0) ? 1u : 0u);
         }
         umma_commit(pv_done);
@@ -167,9 +172,10 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
             issue_S(U + 1);
           }
           mbar_wait(&p_full[U & 1], (U >> 1) & 1, 0x9340 | (U & 1));
+          if (u == 0 && si > 0) mbar_wait(o_free, (si - 1) & 1, 0x9350);   // the previous set's O has been read out
           tc_fence_after();
-          issue_PV(U, si, u == 0);
-          if (U == n_total - 1) umma_commit(o_final);
+          issue_PV(U, u == 0);
+          if (u == ns - 1) umma_commit(o_final);
           umma_commit(&kv_empty[U % STAGES]);   // done with K(U), V(U)
         }
       }
@@ -181,7 +187,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
     const uint32_t lane_sel = uint32_t(quarter * 32) << 16;
     const uint32_t tQ = tmem_base + lane_sel;
     const uint32_t tS = tmem_base + lane_sel + 64;
-    const uint32_t tO0 = tmem_base + lane_sel + 128;
+    const uint32_t tO = tmem_base + lane_sel + 128;
     const int row = q0 + r;
     const bool row_ok = row < p.q_len;
     uint8_t* p_row0 = sP + r * 128;
@@ -211,7 +217,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
     uint64_t lsum2 = pack_f32x2(0.f, 0.f), lsum2b = pack_f32x2(0.f, 0.f);  // two independent row-sum chains
 
     // U: global step (barrier phases, P buffer), u: step inside the current set, MASK: 0 none, 1 ragged tail, 2 window
-    auto step = [&](int U, int u, int kv_len, uint32_t tO, auto mask_tag) {
+    auto step = [&](int U, int u, int kv_len, auto mask_tag) {
       constexpr int MASK = decltype(mask_tag)::value;
       mbar_wait(s_full, U & 1, 0x9400);
       tc_fence_after();
@@ -363,77 +369,67 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
       if (lane == 0) mbar_arrive(&p_full[U & 1]);
     };
 
-    float inv_l[MAX_SETS] = {0.f, 0.f, 0.f};
-    int U = 0;
-#pragma unroll
-    for (int si = 0; si < MAX_SETS; ++si) {
-      if (si < p.n_sets) {
-        const int kv_len = p.kv_len[si];
-        const uint32_t tO = tO0 + si * 128;
-        lsum2 = pack_f32x2(0.f, 0.f);
-        lsum2b = pack_f32x2(0.f, 0.f);
-        if (p.windowed[si]) {
-          step(U, 0, kv_len, tO, std::integral_constant<int, 2>{});
-          ++U;
-        } else {
-          const int ns = (kv_len + SUB - 1) / SUB;
-          for (int u = 0; u < ns - 1; ++u, ++U) step(U, u, kv_len, tO, std::integral_constant<int, 0>{});
-          if (kv_len % SUB) step(U, ns - 1, kv_len, tO, std::integral_constant<int, 1>{});
-          else step(U, ns - 1, kv_len, tO, std::integral_constant<int, 0>{});
-          ++U;
-        }
-        float l_lo, l_hi;
-        lsum2 = add_f32x2(lsum2, lsum2b);
-        unpack_f32x2(lsum2, l_lo, l_hi);
-        inv_l[si] = 1.0f / (l_lo + l_hi);
-      }
-    }
-
-    // ---- epilogue: bf16(O_0 / l_0) (+ bf16(O_1 / l_1)) (+ bf16(O_2 / l_2)) in bf16 adds -> global, written once
-    mbar_wait(o_final, 0, 0x9500);
-    tc_fence_after();
     __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)row * p.o_ls + head * D;
+    int U = 0;
+    for (int si = 0; si < p.n_sets; ++si) {
+      const int kv_len = p.kv_len[si];
+      lsum2 = pack_f32x2(0.f, 0.f);
+      lsum2b = pack_f32x2(0.f, 0.f);
+      if (p.windowed[si]) {
+        step(U, 0, kv_len, std::integral_constant<int, 2>{});
+        ++U;
+      } else {
+        const int ns = (kv_len + SUB - 1) / SUB;
+        for (int u = 0; u < ns - 1; ++u, ++U) step(U, u, kv_len, std::integral_constant<int, 0>{});
+        if (kv_len % SUB) step(U, ns - 1, kv_len, std::integral_constant<int, 1>{});
+        else step(U, ns - 1, kv_len, std::integral_constant<int, 0>{});
+        ++U;
+      }
+      // ---- epilogue of the set: O / l -> bf16 -> (+=) global
+      mbar_wait(o_final, si & 1, 0x9500);
+      tc_fence_after();
+      float l_lo, l_hi;
+      lsum2 = add_f32x2(lsum2, lsum2b);
+      unpack_f32x2(lsum2, l_lo, l_hi);
+      const float inv_l = 1.0f / (l_lo + l_hi);
+      const bool acc = p.accumulate || si > 0;
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-      float y[32];
-      if (p.accumulate && row_ok) {
-#pragma unroll
-        for (int v8 = 0; v8 < 4; ++v8) {
-          const uint4 old = *reinterpret_cast<const uint4*>(orow + cc * 32 + v8 * 8);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&old);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 f = __bfloat1622float2(h[t]);
-            y[v8 * 8 + 2 * t] = f.x;
-            y[v8 * 8 + 2 * t + 1] = f.y;
-          }
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t o[32];
+        tmem_ld_x32(tO + cc * 32, o);
+        tmem_ld_wait();
+        if (cc == 3) {   // all of O is in registers: the next set's first P V may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_free);
         }
-      }
+        if (row_ok) {
+          uint4 old[4];
+          if (acc) {
 #pragma unroll
-      for (int si = 0; si < MAX_SETS; ++si) {
-        if (si < p.n_sets) {
-          uint32_t o[32];
-          tmem_ld_x32(tO0 + si * 128 + cc * 32, o);
-          tmem_ld_wait();
-          const float il = inv_l[si];
-          if (si == 0 && !p.accumulate) {
-#pragma unroll
-            for (int t = 0; t < 32; ++t) y[t] = bf16_round(__uint_as_float(o[t]) * il);
-          } else {
-#pragma unroll
-            for (int t = 0; t < 32; ++t) y[t] = bf16_round(y[t] + bf16_round(__uint_as_float(o[t]) * il));
+            for (int v8 = 0; v8 < 4; ++v8) old[v8] = *reinterpret_cast<const uint4*>(orow + cc * 32 + v8 * 8);
           }
-        }
-      }
-      if (row_ok) {
 #pragma unroll
-        for (int v8 = 0; v8 < 4; ++v8) {
-          uint4 uu;
-          uu.x = pack_bf16x2(y[v8 * 8], y[v8 * 8 + 1]);
-          uu.y = pack_bf16x2(y[v8 * 8 + 2], y[v8 * 8 + 3]);
-          uu.z = pack_bf16x2(y[v8 * 8 + 4], y[v8 * 8 + 5]);
-          uu.w = pack_bf16x2(y[v8 * 8 + 6], y[v8 * 8 + 7]);
-          *reinterpret_cast<uint4*>(orow + cc * 32 + v8 * 8) = uu;
+          for (int v8 = 0; v8 < 4; ++v8) {
+            float y[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(o[v8 * 8 + t]) * inv_l;
+            if (acc) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&old[v8]);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __bfloat1622float2(h[t]);
+                y[2 * t] = f.x + bf16_round(y[2 * t]);
+                y[2 * t + 1] = f.y + bf16_round(y[2 * t + 1]);
+              }
+            }
+            uint4 uu;
+            uu.x = pack_bf16x2(y[0], y[1]);
+            uu.y = pack_bf16x2(y[2], y[3]);
+            uu.z = pack_bf16x2(y[4], y[5]);
+            uu.w = pack_bf16x2(y[6], y[7]);
+            *reinterpret_cast<uint4*>(orow + cc * 32 + v8 * 8) = uu;
+          }
         }
       }
     }
