@@ -8,5 +8,6 @@ timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpuru
 tail -1 gpurun_out/bench.log | cut -c1-3000; tail -3 gpurun_out/bench.err
 SHORT="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph --no-vae"
 timeout 300 $SHORT > gpurun_out/plain.log 2>&1 &&
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 700 --csv --log-file gpurun_out/step_launches.csv $SHORT > gpurun_out/ncu_list.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3400 -c 2400 --csv --log-file gpurun_out/step_launches.csv $SHORT > gpurun_out/ncu_list.log 2>&1
 echo "ncu list exit $?"
+python tools/launch_summary.py gpurun_out/step_launches.csv | head -20
