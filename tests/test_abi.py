@@ -117,3 +117,42 @@ def test_riflex_table_matches_reference(golden_dir):
     assert not torch.equal(m.freqs, base)
     m.disable_riflex()
     assert torch.equal(m.freqs, base)
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_gpu(lib):
+    """Argument validation of the round-1 additions (sequence-parallel exchange, fused cross-attention, fp32 mode,
+    VAE encode helpers) answers before any CUDA call."""
+    from stableavatar_b200 import ops
+    sp = ops.SpArgs()                                    # null source
+    assert lib.sa_sp_scatter_qkv(C.byref(sp), None) == -1
+    sp = ops.SpArgs(src=16, ld=4608, B=1, Ll=8, heads=12, head_dim=128, P=8, rank=0, hg=5)    # 5 does not divide 8
+    assert lib.sa_sp_scatter_qkv(C.byref(sp), None) == -1 and b"hg" in lib.sa_last_error()
+    sp = ops.SpArgs(src=16, ld=4608, B=1, Ll=8, heads=12, head_dim=128, P=2, rank=0, hg=2)    # destinations missing
+    assert lib.sa_sp_scatter_o(C.byref(sp), None) == -1 and b"null destination" in lib.sa_last_error()
+    assert lib.sa_sp_barrier(None, None, 2, 0, None) == -1
+    ca = ops.CrossArgs()
+    assert lib.sa_cross_attn3_d128(C.byref(ca), None) == -1
+    ca = ops.CrossArgs(q=16, out=16, batch=1, heads=1, q_len=128, n_sets=1, scale=1.0, rows_per_group=16)
+    ca.set[0] = ops.CrossSet(k=16, v=16, k_bs=1024, k_ls=128, v_bs=1024, v_ls=128, kv_len=15, kv_total=60, windowed=1)
+    assert lib.sa_cross_attn3_d128(C.byref(ca), None) == -3          # (127 / 16 + 2) windows of 15 keys do not fit one step
+    assert b"windowed" in lib.sa_last_error()
+    assert lib.sa_f32_split3(None, C.c_int64(8), C.c_int64(4), 8, 8, None, 0, None) == -1
+    assert lib.sa_f32_split3(C.c_void_p(16), C.c_int64(8), C.c_int64(4), 8, 4, C.c_void_p(16), 0, None) == -1   # K_pad < K
+    assert lib.sa_f32_softmax_rows(C.c_void_p(16), 4, 8, C.c_int64(4), C.c_float(1.0), None) == -1              # ld < n
+    assert lib.sa_vae_space_to_depth(C.c_void_p(16), C.c_void_p(16), 1, 5, 4, 8, None) == -1                     # odd H
+    h = C.create_string_buffer(64)
+    off = C.c_int64(0)
+    assert lib.sa_ipc_export(None, h, C.byref(off)) == -1
+
+
+def test_14b_state_dict_keys_match_reference_names():
+    from stableavatar_b200 import synth
+    from stableavatar_b200.wan_transformer3d import WanTransformer3DFantasy14BModel
+    cfg = synth.DIT_14B_TINY
+    keys = ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim", "out_dim",
+            "num_heads", "num_layers")
+    m = WanTransformer3DFantasy14BModel(**{k: cfg[k] for k in keys})
+    want = synth.dit_param_shapes(cfg)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == {k: tuple(v) for k, v in want.items()}
+    assert "vocal_projector.proj_model.proj_2.weight" in got and "vocal_projector.proj_model.proj.weight" not in got
