@@ -12,6 +12,7 @@ Mirrors 1B.py:928-1159 (forward), :650-695 (block), :383-413 / :534-605 (attenti
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import torch
 
@@ -49,6 +50,8 @@ def split_weight(w):
     hit = _W_CACHE.get(id(w))
     if hit is None or hit[0] != key:
         w2 = w.reshape(w.shape[0], -1)
+        if hit is None:
+            weakref.finalize(w, _W_CACHE.pop, id(w), None)       # drop the split copy with the parameter
         hit = (key, [split3(w2[:, k0:k1], 1) for k0, k1 in _chunks(w2.shape[1])])
         _W_CACHE[id(w)] = hit
     return hit[1]

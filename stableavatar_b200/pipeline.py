@@ -55,6 +55,23 @@ def overlap_weights(n, scheme, device, dtype):
     return w.view(1, 1, n, 1, 1).to(device=device, dtype=dtype)
 
 
+def _frames_kwarg(transformer, clip_length):
+    """The 1.3B class takes `video_sample_n_frames` (1B.py:939); the train_14B class has no such argument (14B.py:922-933:
+    81 frames / 21 audio groups are hard-wired), so it is passed only where the forward accepts it."""
+    import inspect
+    fwd = getattr(transformer, "forward", transformer)
+    try:
+        params = inspect.signature(fwd).parameters
+    except (TypeError, ValueError):
+        return {"video_sample_n_frames": clip_length}
+    if "video_sample_n_frames" in params or any(p.kind == p.VAR_KEYWORD for p in params.values()):
+        return {"video_sample_n_frames": clip_length}
+    if clip_length != 81:
+        raise ValueError(f"{type(transformer).__name__}.forward is fixed to 81-frame windows (21 latent frames); "
+                         f"got clip_length={clip_length}")
+    return {}
+
+
 class GraphedDenoiseStep:
     """One window of one step — DiT forward on the CFG batch + CFG combine + Euler update — captured once as CUDA
     graph(s) and replayed for every step of that window shape: the ~650 kernel launches of a step (≈ 80 ms of host
@@ -75,7 +92,7 @@ class GraphedDenoiseStep:
             x = self.lat.expand(n, -1, -1, -1, -1).contiguous() if n > 1 else self.lat
             pred = pipe.transformer(x=x, context=prompt_embeds, t=self.t, seq_len=seq_len, y=y[:, :, :self.lat.size(2)],
                                     clip_fea=clip_context, vocal_embeddings=self.vocal, is_clip_level_modeling=False,
-                                    video_sample_n_frames=clip_length)
+                                    **_frames_kwarg(pipe.transformer, clip_length))
             return ops.cfg_euler_step(pred.contiguous(), self.lat, 0.0, audio_scale=float(audio_guide_scale or 0.0),
                                       text_scale=float(text_guide_scale or 0.0), cfg=do_cfg, dsigma_dev=self.ds)
 
@@ -126,7 +143,7 @@ class WanI2VTalkingInferenceLongPipeline:
         tt = t.expand(n) if torch.is_tensor(t) else torch.full((n,), float(t), device=latents.device)
         noise_pred = self.transformer(x=x, context=prompt_embeds, t=tt, seq_len=seq_len, y=y[:, :, :latents.size(2)],
                                       clip_fea=clip_context, vocal_embeddings=vocal_embeddings,
-                                      is_clip_level_modeling=False, video_sample_n_frames=clip_length)
+                                      is_clip_level_modeling=False, **_frames_kwarg(self.transformer, clip_length))
         if fp32:
             from . import fp32_mode
             step = fp32_mode.cfg_euler_step

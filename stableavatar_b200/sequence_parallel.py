@@ -200,6 +200,19 @@ class PeerExchange:
         self.kv_ptrs, self.q_ptrs, self.o_ptrs, self.sig_ptrs = ptrs
         dist.barrier(group=group)                               # every rank has mapped every buffer before the first store
 
+    def close(self):
+        """Unmap the peers' allocations (the local buffers are ordinary tensors). Call on every rank once no rank will
+        store into another any more; also runs when the object is collected."""
+        bases, self._bases = getattr(self, "_bases", {}), {}
+        for base in bases.values():
+            try:
+                ops.ipc_close(base)
+            except Exception:  # noqa: BLE001  (context already torn down at interpreter exit)
+                pass
+
+    def __del__(self):
+        self.close()
+
     def barrier(self):
         ops.sp_barrier(self.sig_ptrs, self.epoch, self.pl.world, self.pl.rank)
 

@@ -69,3 +69,22 @@ def test_vae_pipeline_partition():
     assert max(sum(costs[a:b]) for a, b in part(costs, 3)) == 8
     assert max(sum(costs[a:b]) for a, b in part(costs, 2)) == 12
     assert part([5.0], 4) == [(0, 1), (1, 1), (1, 1), (1, 1)]
+
+
+def test_frames_kwarg_only_where_the_forward_takes_it():
+    """The 14B class's forward has no video_sample_n_frames (14B.py:922-933): the pipeline must not pass it, and must
+    refuse window lengths other than the hard-wired 81 frames."""
+    import pytest
+    from stableavatar_b200.pipeline import _frames_kwarg
+    from stableavatar_b200.wan_transformer3d import WanTransformer3DFantasy14BModel, WanTransformer3DFantasyModel
+
+    class Obj:
+        pass
+    one, big = Obj(), Obj()
+    one.forward = WanTransformer3DFantasyModel.forward.__get__(one)
+    big.forward = WanTransformer3DFantasy14BModel.forward.__get__(big)
+    assert _frames_kwarg(one, 33) == {"video_sample_n_frames": 33}
+    assert _frames_kwarg(big, 81) == {}
+    with pytest.raises(ValueError, match="81-frame"):
+        _frames_kwarg(big, 33)
+    assert _frames_kwarg(lambda **kw: None, 9) == {"video_sample_n_frames": 9}
