@@ -211,7 +211,9 @@ class PeerExchange:
                 pass
 
     def __del__(self):
-        self.close()
+        import sys
+        if not sys.is_finalizing():          # at interpreter exit the CUDA context unmaps everything itself
+            self.close()
 
     def barrier(self):
         ops.sp_barrier(self.sig_ptrs, self.epoch, self.pl.world, self.pl.rank)
