@@ -88,3 +88,26 @@ def test_frames_kwarg_only_where_the_forward_takes_it():
     with pytest.raises(ValueError, match="81-frame"):
         _frames_kwarg(big, 33)
     assert _frames_kwarg(lambda **kw: None, 9) == {"video_sample_n_frames": 9}
+
+
+@pytest.mark.parametrize("n", [10, 50])
+def test_scheduler_tables_against_real_diffusers_when_installed(n):
+    """the scheduler restatement is 'parity unpinned' because diffusers (reference dependency, pinned
+    0.30.1) is not in this image. Wherever a real diffusers is importable, pin sigma / timestep tables and one step."""
+    import sys
+    mod = sys.modules.get("diffusers")
+    if mod is not None and getattr(mod, "_sa_stub", False):
+        pytest.skip("only the oracle's import stub of diffusers is present")
+    diffusers = pytest.importorskip("diffusers")
+    from oracle import pipeline as OP
+    from stableavatar_b200.scheduler import FlowMatchEulerDiscreteScheduler
+    ref = diffusers.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=5.0)
+    ref.set_timesteps(n)
+    mine = FlowMatchEulerDiscreteScheduler(1000, 5.0)
+    mine.set_timesteps(n)
+    sig, ts = OP.flow_match_sigmas(n)
+    assert torch.allclose(ref.sigmas.float(), sig, atol=1e-6) and torch.allclose(ref.timesteps.float(), ts, atol=1e-3)
+    assert torch.allclose(mine.sigmas.float().cpu(), sig, atol=1e-6)
+    x, v = torch.randn(1, 4, 2, 3, 3), torch.randn(1, 4, 2, 3, 3)
+    want = ref.step(v, ref.timesteps[0], x, return_dict=False)[0]
+    assert torch.allclose(OP.euler_step(v, x, sig[0], sig[1]), want, atol=1e-6)
