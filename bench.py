@@ -26,7 +26,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "s/denoise-step 1.3B @480x832x81f"
-SELF_ATTN_DRAM_BYTES_B3 = 913.43e6 + 285.35e6   # measured once with ncu on this command, see profiles/
+SELF_ATTN_DRAM_BYTES_B3 = 918.55e6 + 288.42e6   # ncu --set full of one flash_attn_v8_kernel launch inside bench.py (profiles/r01_selfattn_in_bench_ncu.txt)
 UNIT = "s/step"
 
 
@@ -323,7 +323,7 @@ def run_b200(args):
                        "vae_decode_s": None, "clip_s": None,
                        "clip_s_note": "50 denoise steps x value + one VAE decode (21x60x104 latent -> 81x480x832)"
                                       + (f", decoder pipelined over the {world} GPUs (bit-identical frames)" if world > 1 else "")},
-            "roofline": {"kernel": "flash_attn_d128_kernel (self-attention)", "bound": "tensor", "achieved": achieved,
+            "roofline": {"kernel": "attn8::flash_attn_v8_kernel (self-attention, sa_flash_attn_d128)", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"] if achieved else None,
                          "traffic": SELF_ATTN_DRAM_BYTES_B3 / world if (args.frames, args.height, args.width) == (81, 480, 832) else None,
                          "traffic_source": "profiles/r01_selfattn_in_bench_ncu.txt (ncu --set full, dram__bytes_read+write of one "
