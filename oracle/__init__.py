@@ -1,0 +1,1 @@
+"""CPU oracles (test infrastructure only): restatements of the reference algorithms, pinned by tests/golden/."""

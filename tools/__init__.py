@@ -1,0 +1,1 @@
+"""Developer tools: golden-fixture generators, GPU check / profiling scripts."""
