@@ -252,6 +252,12 @@ typedef struct {
 int sa_sp_scatter_qkv(const sa_sp_args* args, sa_stream_t stream);
 int sa_sp_scatter_o(const sa_sp_args* args, sa_stream_t stream);
 int sa_sp_barrier(void* const* sig, void* epoch, int32_t P, int32_t rank, sa_stream_t stream);
+/* Producer fusion of sa_rmsnorm_rope + sa_sp_scatter_qkv: q and k of the fused QKV rows (args->src, un-normalised) get the
+ * WanRMSNorm + 3-D RoPE of 1B.py:296-342 (token index = tok_offset + row % Ll, same arithmetic and rounding as
+ * sa_rmsnorm_rope), v is copied, and every chunk goes straight to its destination rank's kv_recv / q_recv (layouts as
+ * above). The local rows are left untouched. weight_q / weight_k: bf16 [heads * 128]; freqs as in sa_rms_args. */
+int sa_sp_norm_rope_scatter(const sa_sp_args* args, const void* weight_q, const void* weight_k, const void* freqs,
+                            int32_t F, int32_t H, int32_t W, int32_t tok_offset, float eps, sa_stream_t stream);
 /* CUDA IPC for the mappings above. sa_ipc_export: 64-byte handle of the cudaMalloc allocation containing ptr + the byte
  * offset of ptr inside it. sa_ipc_open: map a PEER process's allocation; call with the device that will launch the
  * scatter kernels current (peer access is enabled for that device); returns the allocation base. sa_ipc_close unmaps. */

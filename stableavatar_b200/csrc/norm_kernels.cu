@@ -277,6 +277,100 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 8 ? 4 : 2) rmsnor
   }
 }
 
+// ------------------------------------------------------------------------------------------------ RMSNorm + RoPE + scatter
+// Sequence-parallel producer fusion: the same arithmetic as rmsnorm_rope_kernel on the q and k parts of a fused QKV row
+// (v is copied), but every 16-byte chunk is stored straight into its destination rank's receive buffer over NVLink
+// (layouts and destination arithmetic of sp_exchange.cu's scatter_qkv_kernel) instead of back into the local row —
+// the normalised q / k never make a local round trip and the separate scatter launch disappears.
+struct RmsScatterParams {
+  const __nv_bfloat16* qkv;        // [B*Ll, ld] rows: q | k | v, each C = heads * 128 wide
+  const __nv_bfloat16* weight[2];  // norm_q, norm_k
+  const float2* freqs;
+  uint4* kv_dst[8];
+  uint4* q_dst[8];
+  long long ld;
+  int rows, C, Ll, B, F, H, W, tok_offset;
+  int nh, P, rank, qs, hp;
+  float eps;
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 8 ? 4 : 2) rmsnorm_rope_scatter_kernel(const RmsScatterParams p) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int which = blockIdx.y;  // 0 q, 1 k, 2 v
+  const __nv_bfloat16* x = p.qkv + which * p.C;
+  const int nchunks = p.C >> 3;
+  RowChunk<true> v[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + c * 32;
+    if (ch < nchunks) v[c].load(x, (long long)row * p.ld + ch * 8);
+  }
+  float rinv = 0.f;
+  if (which < 2) {
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (lane + c * 32 < nchunks) {
+        float t[8];
+        v[c].get(t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += t[i] * t[i];
+      }
+    }
+    rinv = rsqrtf(warp_sum(ss) / p.C + p.eps);
+  }
+  const int t_loc = row % p.Ll, b = row / p.Ll;
+  const int tok = t_loc + p.tok_offset;
+  const bool rotate = which < 2 && p.freqs != nullptr && tok < p.F * p.H * p.W;
+  const int pf = tok / (p.H * p.W), ph = (tok / p.W) % p.H, pw = tok % p.W;
+  const int s_me = p.rank % p.qs;
+  const long long q_row = ((long long)(p.rank / p.qs) * p.Ll + t_loc) * p.B + b;   // row index inside q_recv
+  const long long kv_row = ((long long)p.rank * p.Ll + t_loc) * p.B + b;           // row index inside kv_recv
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + c * 32;
+    if (ch >= nchunks) continue;
+    const int col = ch * 8;
+    uint4 outv;
+    if (which < 2) {
+      float w[8], y[8];
+      load8_bf16(p.weight[which] + col, w);
+      v[c].get(y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = bf16_round(bf16_round(y[i] * rinv) * w[i]);
+      if (rotate) {
+        const int j0 = (col & 127) >> 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = j0 + i;
+          const int pos = j < 22 ? pf : (j < 43 ? ph : pw);
+          const float2 cs = __ldg(&p.freqs[pos * 64 + j]);
+          const float a = y[2 * i], bb = y[2 * i + 1];
+          y[2 * i] = a * cs.x - bb * cs.y;
+          y[2 * i + 1] = a * cs.y + bb * cs.x;
+        }
+      }
+      outv.x = pack_bf16x2(y[0], y[1]);
+      outv.y = pack_bf16x2(y[2], y[3]);
+      outv.z = pack_bf16x2(y[4], y[5]);
+      outv.w = pack_bf16x2(y[6], y[7]);
+    } else {
+      outv = v[c].u;
+    }
+    const int h = ch >> 4, c16 = ch & 15;   // 16 chunks of 16 bytes per 128-wide head
+    const int g = h / p.hp, hl = h % p.hp;
+    if (which == 0) {
+      p.q_dst[g * p.qs + s_me][(q_row * p.hp + hl) * 16 + c16] = outv;
+    } else {
+      const long long off = ((kv_row * 2 + (which - 1)) * p.hp + hl) * 16 + c16;
+      for (int s = 0; s < p.qs; ++s) p.kv_dst[g * p.qs + s][off] = outv;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ broadcast add
 // out[i, j, :] = bf16(a[i, :] + b[j, :])   — e = modulation + e0 for every block at once (1B.py:672)
 __global__ void add_bcast_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* out, int na, int nb,
@@ -379,5 +473,44 @@ extern "C" int sa_add_bcast_bf16(const void* a, const void* b, void* out, int32_
                                                    reinterpret_cast<__nv_bfloat16*>(out), na, nb, n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "add_bcast_kernel launch");
+  return SA_OK;
+}
+
+extern "C" int sa_sp_norm_rope_scatter(const sa_sp_args* a, const void* weight_q, const void* weight_k, const void* freqs,
+                                       int32_t F, int32_t H, int32_t W, int32_t tok_offset, float eps, sa_stream_t stream_) {
+  using namespace sa;
+  using namespace sa::norm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->src || !weight_q || !weight_k || a->P < 1 || a->P > 8 || a->rank < 0 || a->rank >= a->P || a->B <= 0 || a->Ll <= 0 ||
+      a->heads <= 0 || a->hg <= 0 || a->P % a->hg || a->heads % a->hg || a->head_dim != 128) {
+    set_error("sa_sp_norm_rope_scatter: bad argument (1 <= P <= 8, hg | P, hg | heads, head_dim 128)");
+    return SA_ERR_BAD_ARG;
+  }
+  const int C = a->heads * 128;
+  if (C > MAX_CHUNKS * 256 || a->ld % 8 || a->ld < 3LL * C) {
+    set_error("sa_sp_norm_rope_scatter: heads * 128 <= %d, ld %% 8 == 0, ld >= 3 * heads * 128", MAX_CHUNKS * 256);
+    return SA_ERR_BAD_ARG;
+  }
+  if (freqs && (F <= 0 || H <= 0 || W <= 0 || F > 1024 || H > 1024 || W > 1024)) { set_error("sa_sp_norm_rope_scatter: bad RoPE grid"); return SA_ERR_BAD_ARG; }
+  RmsScatterParams p;
+  p.qkv = reinterpret_cast<const __nv_bfloat16*>(a->src);
+  p.weight[0] = reinterpret_cast<const __nv_bfloat16*>(weight_q);
+  p.weight[1] = reinterpret_cast<const __nv_bfloat16*>(weight_k);
+  p.freqs = reinterpret_cast<const float2*>(freqs);
+  for (int r = 0; r < 8; ++r) {
+    p.kv_dst[r] = r < a->P ? reinterpret_cast<uint4*>(a->dst_a[r]) : nullptr;
+    p.q_dst[r] = r < a->P ? reinterpret_cast<uint4*>(a->dst_b[r]) : nullptr;
+    if (r < a->P && (!p.kv_dst[r] || !p.q_dst[r])) { set_error("sa_sp_norm_rope_scatter: null destination for rank %d", r); return SA_ERR_BAD_ARG; }
+  }
+  p.ld = a->ld; p.rows = a->B * a->Ll; p.C = C; p.Ll = a->Ll; p.B = a->B; p.F = F; p.H = H; p.W = W; p.tok_offset = tok_offset;
+  p.nh = a->heads; p.P = a->P; p.rank = a->rank; p.qs = a->P / a->hg; p.hp = a->heads / a->hg; p.eps = eps;
+  dim3 grid((p.rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 3);
+  const int nch = (C / 8 + 31) / 32;
+  if (nch <= 2) rmsnorm_rope_scatter_kernel<2><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  else if (nch <= 6) rmsnorm_rope_scatter_kernel<6><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  else if (nch <= 8) rmsnorm_rope_scatter_kernel<8><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  else rmsnorm_rope_scatter_kernel<20><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "rmsnorm_rope_scatter_kernel launch");
   return SA_OK;
 }

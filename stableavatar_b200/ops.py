@@ -419,3 +419,17 @@ def cross_attn3(q, sets, out=None, accumulate=False, rows_per_group=0, tok_offse
                             kv_len=window if window else k.shape[1], kv_total=k.shape[1], windowed=int(bool(window)))
     L.check(L.lib().sa_cross_attn3_d128(C.byref(a), L.stream_ptr()), "sa_cross_attn3_d128")
     return out
+
+
+def sp_norm_rope_scatter(qkv, weight_q, weight_k, kv_ptrs, q_ptrs, *, B, Ll, heads, P, rank, hg, freqs=None, grid=(1, 1, 1),
+                         tok_offset=0, eps=1e-6):
+    """RMSNorm + RoPE of the q / k parts of local QKV rows fused with the peer scatter — sa_sp_norm_rope_scatter."""
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[0] == B * Ll
+    assert weight_q.dtype == weight_k.dtype == torch.bfloat16
+    if freqs is not None:
+        assert freqs.dtype == torch.float32 and freqs.shape == (1024, 64, 2) and freqs.is_contiguous()
+    a = _sp_args(qkv, kv_ptrs, q_ptrs, qkv.stride(0), B, Ll, heads, P, rank, hg)
+    L.check(L.lib().sa_sp_norm_rope_scatter(C.byref(a), C.c_void_p(weight_q.data_ptr()), C.c_void_p(weight_k.data_ptr()),
+                                            C.c_void_p(L.ptr(freqs)), grid[0], grid[1], grid[2], tok_offset, C.c_float(eps),
+                                            L.stream_ptr()), "sa_sp_norm_rope_scatter")

@@ -227,6 +227,17 @@ class PeerExchange:
             self.barrier()
         return (self.q_recv.view(len(pl.q_sources) * Ll, B, pl.hp, d), self.kv_recv.view(pl.world * Ll, B, 2, pl.hp, d))
 
+    def norm_rope_exchange_qkv(self, qkv, weight_q, weight_k, freqs, grid, tok_offset):
+        """exchange_qkv with the RMSNorm + RoPE of q / k fused into the scatter: qkv holds the raw projection rows, the
+        normalised values only ever exist in the receive buffers."""
+        B, Ll, nh, d = self.shape
+        pl = self.pl
+        with ops.timed("sp_a2a_qkv"):
+            ops.sp_norm_rope_scatter(qkv, weight_q, weight_k, self.kv_ptrs, self.q_ptrs, B=B, Ll=Ll, heads=nh, P=pl.world,
+                                     rank=pl.rank, hg=pl.hg, freqs=freqs, grid=grid, tok_offset=tok_offset)
+            self.barrier()
+        return (self.q_recv.view(len(pl.q_sources) * Ll, B, pl.hp, d), self.kv_recv.view(pl.world * Ll, B, 2, pl.hp, d))
+
     def exchange_out(self, O):
         B, Ll, nh, d = self.shape
         pl = self.pl
@@ -234,6 +245,12 @@ class PeerExchange:
             ops.sp_scatter_o(O, self.o_ptrs, B=B, Ll=Ll, heads=nh, P=pl.world, rank=pl.rank, hg=pl.hg)
             self.barrier()
         return self.o_recv.view(B, Ll, nh, d)
+
+
+def _fused_norm():
+    """SA_SP_FUSED_NORM=1: RMSNorm + RoPE of q / k fused into the peer scatter (sa_sp_norm_rope_scatter)."""
+    import os
+    return os.environ.get("SA_SP_FUSED_NORM", "0") == "1"
 
 
 def _peer_exchange(model, B, Ll, nh, d, device):
@@ -265,14 +282,17 @@ def self_attention(model, qkv, sa, st):
     sequence for this rank's heads, all-to-all back. Returns [B, Ll, nh, 128]."""
     B, C, nh, Ll = st["B"], st["C"], st["nh"], st["Ll"]
     pl = model._sp
-    ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
-                      grid=st["grid"], rows_per_batch=Ll, tok_offset=st["tok0"])
     px = _peer_exchange(model, B, Ll, nh, 128, qkv.device)
-    if px is not None:
-        Q, KV = px.exchange_qkv(qkv)
+    if px is not None and _fused_norm():
+        Q, KV = px.norm_rope_exchange_qkv(qkv, sa.norm_q.weight, sa.norm_k.weight, st["freqs"], st["grid"], st["tok0"])
     else:
-        q5 = qkv.view(B, Ll, 3, nh, 128)
-        Q, KV = exchange_qkv(pl, q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], model.sp_group, kv=q5[:, :, 1:3])
+        ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
+                          grid=st["grid"], rows_per_batch=Ll, tok_offset=st["tok0"])
+        if px is not None:
+            Q, KV = px.exchange_qkv(qkv)
+        else:
+            q5 = qkv.view(B, Ll, 3, nh, 128)
+            Q, KV = exchange_qkv(pl, q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], model.sp_group, kv=q5[:, :, 1:3])
     with ops.timed("self_attn"):
         O = ops.flash_attn(Q.transpose(0, 1), KV[:, :, 0].transpose(0, 1), KV[:, :, 1].transpose(0, 1),
                            out=torch.empty_like(Q).transpose(0, 1))

@@ -37,6 +37,24 @@ log("peer buffers mapped")
 Qp, KVp = px.exchange_qkv(qkv)
 torch.cuda.synchronize()
 log("peer qkv exchange: Q equal", torch.equal(Qp, Qn), "KV equal", torch.equal(KVp, KVn))
+# producer fusion: RMSNorm + RoPE inside the scatter == sa_rmsnorm_rope in place followed by the plain scatter
+from stableavatar_b200 import ops  # noqa: E402
+C = nh * d
+wq = (1 + 0.1 * torch.randn(C, device=dev, generator=g)).bfloat16()
+wk = (1 + 0.1 * torch.randn(C, device=dev, generator=g)).bfloat16()
+Fg, Hg, Wg = 21, 30, 52
+ang = torch.rand(1024, 64, device=dev, generator=g) * 6.28
+freqs = torch.stack([ang.cos(), ang.sin()], -1).float().contiguous()
+ref = qkv.clone()
+ops.rmsnorm_rope_(ref[:, :C], wq, ref[:, C:2 * C], wk, freqs=freqs, grid=(Fg, Hg, Wg), rows_per_batch=Ll, tok_offset=rank * Ll)
+Qr, KVr = px.exchange_qkv(ref)
+Qr, KVr = Qr.clone(), KVr.clone()
+torch.cuda.synchronize()
+dist.barrier()
+Qf, KVf = px.norm_rope_exchange_qkv(qkv, wq, wk, freqs, (Fg, Hg, Wg), rank * Ll)
+torch.cuda.synchronize()
+log("fused norm+rope+scatter: Q equal", torch.equal(Qf, Qr), "KV equal", torch.equal(KVf, KVr))
+dist.barrier()
 O = torch.randn(Qn.shape, device=dev, generator=g).bfloat16()
 On = sp.exchange_out(pl, O, B, Ll, nh, d, None).contiguous()
 torch.cuda.synchronize()
@@ -64,6 +82,14 @@ t_n = timeit(lambda: sp.exchange_qkv(pl, q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], 
 t_p = timeit(lambda: px.exchange_qkv(qkv))
 log(f"qkv exchange: nccl (pack + 2 all_to_all) {t_n:.3f} ms, peer (scatter + barrier) {t_p:.3f} ms, ~{out_mb:.0f} MB leave the GPU -> "
     f"{out_mb / 1024 / t_p * 1e3:.0f} GiB/s")
+def unfused():
+    ops.rmsnorm_rope_(ref[:, :C], wq, ref[:, C:2 * C], wk, freqs=freqs, grid=(Fg, Hg, Wg), rows_per_batch=Ll, tok_offset=rank * Ll)
+    px.exchange_qkv(ref)
+
+
+t_u = timeit(unfused)
+t_f = timeit(lambda: px.norm_rope_exchange_qkv(qkv, wq, wk, freqs, (Fg, Hg, Wg), rank * Ll))
+log(f"rmsnorm+rope then scatter+barrier {t_u:.3f} ms, fused {t_f:.3f} ms")
 t_n = timeit(lambda: sp.exchange_out(pl, O, B, Ll, nh, d, None).contiguous())
 t_p = timeit(lambda: px.exchange_out(O))
 log(f"O exchange: nccl (all_to_all + unpack) {t_n:.3f} ms, peer {t_p:.3f} ms")
