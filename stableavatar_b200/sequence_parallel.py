@@ -16,6 +16,7 @@ windows. L must be a multiple of P (the model rounds seq_len up, 1B.py:980-981).
 from __future__ import annotations
 
 import math
+import sys
 from types import SimpleNamespace
 
 import torch
@@ -211,9 +212,11 @@ class PeerExchange:
                 pass
 
     def __del__(self):
-        import sys
-        if not sys.is_finalizing():          # at interpreter exit the CUDA context unmaps everything itself
-            self.close()
+        try:
+            if not sys.is_finalizing():      # at interpreter exit the CUDA context unmaps everything itself
+                self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
     def barrier(self):
         ops.sp_barrier(self.sig_ptrs, self.epoch, self.pl.world, self.pl.rank)
@@ -248,9 +251,9 @@ class PeerExchange:
 
 
 def _fused_norm():
-    """SA_SP_FUSED_NORM=1: RMSNorm + RoPE of q / k fused into the peer scatter (sa_sp_norm_rope_scatter)."""
+    """RMSNorm + RoPE of q / k fused into the peer scatter (sa_sp_norm_rope_scatter); SA_SP_FUSED_NORM=0 keeps them apart."""
     import os
-    return os.environ.get("SA_SP_FUSED_NORM", "0") == "1"
+    return os.environ.get("SA_SP_FUSED_NORM", "1") != "0"
 
 
 def _peer_exchange(model, B, Ll, nh, d, device):

@@ -23,8 +23,9 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q_out, peer):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SA_SP_PEER=peer)
+def _worker(rank, world, port, q_out, mode):
+    peer, fused = mode[0], mode[1]          # "11": peer stores with fused norm+rope, "10": peer stores, "00": NCCL
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SA_SP_PEER=peer, SA_SP_FUSED_NORM=fused)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -51,7 +52,7 @@ def _worker(rank, world, port, q_out, peer):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("peer", ["1", "0"])
+@pytest.mark.parametrize("peer", ["11", "10", "00"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sp_forward_equals_single_gpu(world, peer):
     if torch.cuda.device_count() < world:
