@@ -2,9 +2,12 @@
 wan/pipeline/wan_inference_long_pipeline.py:704-791 and of diffusers==0.30.1's FlowMatchEulerDiscreteScheduler
 (reference dependency, pyproject.toml:15; not vendored and not installed here).
 
-PARITY UNPINNED for the scheduler arithmetic: the reference holds no test or golden vector for it and diffusers
-cannot be imported on this box; the restatement follows the published 0.30.1 source. The loop itself is written with
-plain Python lists / torch ops exactly in the reference's statement order so that the product's restructured loop
+PARITY UNPINNED for the scheduler arithmetic only: the reference holds no test or golden vector for it and diffusers
+cannot be imported on this box; the restatement follows the published 0.30.1 source (tests/test_pipeline_cpu.py pins it
+against a real diffusers wherever one is importable). The loop and the whole `__call__` chain ARE pinned:
+tests/golden/pipeline_tiny.npz was written by the real reference pipeline class (tools/gen_golden_pipeline.py) and
+`pipeline_call` below reproduces its latents to 4 bf16 ulp-flips in 5120 values. The loop is written with plain Python
+lists / torch ops in the reference's statement order so that the product's restructured loop
 (stableavatar_b200/pipeline.py) can be compared against it on any model callable.
 """
 from __future__ import annotations
@@ -82,3 +85,61 @@ def denoise_loop(model_fn, latents_all, num_inference_steps, clip_length, overla
                 arrive_last = True
         latents_all = pred_latents
     return latents_all
+
+
+def pipeline_call(dit_forward, vae_encode, vae_decode, cfg, *, tokenizer, text_encoder, clip_image_encoder, wav2vec_processor,
+                  wav2vec, prompt, negative_prompt, height, width, clip_length, num_inference_steps, latents, vocal_input_values,
+                  fps, sr, cond_file_path, overlap_window_length, text_guide_scale, audio_guide_scale, scheme="uniform",
+                  max_sequence_length=512, return_latents=False):
+    """Restatement of WanI2VTalkingInferenceLongPipeline.__call__ (pipe.py:540-806) for guidance_scale > 1 on the CPU
+    oracles: `dit_forward(x, t, context, seq_len, clip_fea, y, vocal, video_sample_n_frames)`, `vae_encode(pixels)` ->
+    [B, 32, T', h, w] (first 16 channels = mode), `vae_decode(latents)` -> [B, 3, T, H, W]. Pinned by
+    tests/golden/pipeline_tiny.npz, which the REAL reference pipeline class wrote (tools/gen_golden_pipeline.py)."""
+    from PIL import Image
+
+    def t5(p):                                                                       # pipe.py:241-279
+        tok = tokenizer([p], padding="max_length", max_length=max_sequence_length, truncation=True, add_special_tokens=True,
+                        return_tensors="pt")
+        lens = tok.attention_mask.gt(0).sum(dim=1).long()
+        emb = text_encoder(tok.input_ids, attention_mask=tok.attention_mask)[0].float()
+        return [u[:v] for u, v in zip(emb, lens)]
+    pos, neg = t5(prompt), t5(negative_prompt or "")
+    prompt_embeds = neg + neg + pos                                                  # pipe.py:636
+
+    fpb = (clip_length - 1) // 4 + 1
+    apf = int(sr / fps)
+    max_audio_index = vocal_input_values.shape[0]
+    latents_all = latents.clone()
+    infer_length = latents_all.shape[2]
+
+    img = Image.open(cond_file_path).convert("RGB").resize([width, height])          # pipe.py:661-673
+    arr = (torch.from_numpy(np.array(img)).permute(2, 0, 1) / 255 - 0.5) * 2
+    cond_image = arr.unsqueeze(1).unsqueeze(0)
+    clip_context = torch.cat([clip_image_encoder([arr[:, None, :, :]])] * 3, dim=0)
+    pixels = torch.cat([cond_image, torch.zeros(1, 3, clip_length - 1, height, width)], dim=2).float()
+    masked = vae_encode(pixels)[:, :16]                                              # .mode(), pipe.py:402-403
+    lh, lw = masked.shape[-2:]
+    msk = torch.ones(1, clip_length, lh, lw)
+    msk[:, 1:] = 0
+    msk = torch.cat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:]], dim=1)
+    msk = msk.view(1, msk.shape[1] // 4, 4, lh, lw).transpose(1, 2).float()
+    y = torch.cat([torch.cat([msk] * 3), torch.cat([masked] * 3)], dim=1)
+    seq_len = int(np.ceil((width // 8) * (height // 8) / 4 * fpb))                   # pipe.py:735
+
+    def model_fn(lat, t, index_start, index_end, is_last):                           # pipe.py:714-750
+        a0 = index_start * 4 * apf
+        a1 = max_audio_index if is_last else a0 + (index_end - index_start) * 4 * apf
+        sub = vocal_input_values[[ii % max_audio_index for ii in range(a0, a1)]]
+        vals = wav2vec_processor(sub, sampling_rate=sr, return_tensors="pt").input_values
+        feats = wav2vec(vals).last_hidden_state.float()
+        vocal = torch.cat([torch.zeros_like(feats), feats, feats], dim=0)
+        return dit_forward(torch.cat([lat] * 3), t.expand(3), prompt_embeds, seq_len, clip_context,
+                           y[:, :, :lat.shape[2]], vocal, clip_length)
+
+    # the reference rounds every window's latents to bf16 before writing them back, whatever the weight dtype (pipe.py:774, 779)
+    lat = denoise_loop(model_fn, latents_all, num_inference_steps, clip_length, overlap_window_length, scheme=scheme,
+                       audio_scale=audio_guide_scale, text_scale=text_guide_scale, dtype=torch.bfloat16)
+    lat = lat.float()[:, :, :infer_length]
+    if return_latents:
+        return lat
+    return (vae_decode(lat) / 2 + 0.5).clamp(0, 1)                                   # pipe.py:424-430

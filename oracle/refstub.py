@@ -74,6 +74,9 @@ class _AEOutput:
     def __init__(self, latent_dist):
         self.latent_dist = latent_dist
 
+    def __getitem__(self, i):                      # diffusers' BaseOutput indexes like a tuple of its fields
+        return (self.latent_dist,)[i]
+
 
 def install_stubs():
     if "diffusers" in sys.modules and not getattr(sys.modules["diffusers"], "_sa_stub", False):

@@ -188,7 +188,7 @@ class WanI2VTalkingInferenceLongPipeline:
                     s_idx = [ii % latents.shape[2] for ii in range(overlap_window_length)]
                     e_idx = [ii % n_lat for ii in range(prev_end - overlap_window_length, prev_end)]
                     latents[:, :, s_idx] = latents[:, :, s_idx] * ow + pred_latents[:, :, e_idx] * (1 - ow)
-                latents = latents.to(latents_all.dtype)
+                latents = latents.to(torch.bfloat16).to(pred_latents.dtype)   # the bf16 write-back is hard-wired, pipe.py:774/779
                 pred_latents[:, :, [(ws + k) % n_lat for k in range(latents.size(2))]] = latents
             latents_all = pred_latents
             if callback is not None:

@@ -111,3 +111,38 @@ def test_scheduler_tables_against_real_diffusers_when_installed(n):
     x, v = torch.randn(1, 4, 2, 3, 3), torch.randn(1, 4, 2, 3, 3)
     want = ref.step(v, ref.timesteps[0], x, return_dict=False)[0]
     assert torch.allclose(OP.euler_step(v, x, sig[0], sig[1]), want, atol=1e-6)
+
+
+def test_oracle_pipeline_chain_vs_real_reference_pipeline(golden_dir):
+    """tests/golden/pipeline_tiny.npz was written by the REAL WanI2VTalkingInferenceLongPipeline.__call__ (fp32, CPU; real
+    DiT and VAE classes, stubbed context producers — tools/gen_golden_pipeline.py): 17 frames, three overlapping 9-frame
+    windows, 2 steps, 3-way CFG, VAE encode of the conditioning clip and VAE decode. The oracle chain must reproduce it."""
+    import math
+    from oracle import dit as O, vae as OV
+    from stableavatar_b200 import synth
+    from tools import pipeline_stubs as S
+    gold = np.load(golden_dir / "pipeline_tiny.npz")
+    cfg = synth.DIT_TINY
+    sd, sd_vae = synth.dit_state_dict(cfg), synth.vae_state_dict(encoder=True)
+    c = S.case()
+    S.write_cond_image(c["cond_path"], c["height"], c["width"])
+
+    def dit_forward(x, t, context, seq_len, clip_fea, y, vocal, frames):
+        return O.dit_forward(sd, cfg, x, t, context, seq_len, clip_fea, y, vocal, frames)
+    kw = dict(tokenizer=S.Tokenizer(), text_encoder=S.TextEncoder(cfg["text_dim"]), clip_image_encoder=S.ClipEncoder(),
+              wav2vec_processor=S.Wav2VecProcessor(), wav2vec=S.Wav2Vec(), prompt=c["prompt"],
+              negative_prompt=c["negative_prompt"], height=c["height"], width=c["width"], clip_length=c["clip_length"],
+              num_inference_steps=c["steps"], latents=c["latents"], vocal_input_values=c["audio"], fps=c["fps"], sr=c["sr"],
+              cond_file_path=c["cond_path"], overlap_window_length=c["overlap"], text_guide_scale=c["text_scale"],
+              audio_guide_scale=c["audio_scale"])
+    with torch.no_grad():
+        lat = OP.pipeline_call(dit_forward, lambda p: OV.vae_encode(sd_vae, p), lambda z: OV.vae_decode(sd_vae, z), cfg,
+                               return_latents=True, **kw)
+        video = (OV.vae_decode(sd_vae, lat) / 2 + 0.5).clamp(0, 1)
+    ref_lat = torch.from_numpy(gold["latents"])
+    assert lat.shape == ref_lat.shape == (1, 16, 5, 8, 8)
+    err = ((lat.double() - ref_lat.double()).norm() / ref_lat.double().norm()).item()
+    assert err < 2e-3, err                      # bf16 write-back of every window: an occasional 1-ulp flip is all that may differ
+    ref_video = torch.from_numpy(gold["video_f16"].astype(np.float32))
+    mse = ((video.double() - ref_video.double()) ** 2).mean().item()
+    assert 10 * math.log10(1.0 / mse) > 45.0
