@@ -1,5 +1,4 @@
 """Single self-attention-shaped launch for ncu (B=1, H=12, L=32760, d=128)."""
-import ctypes as C
 import sys
 import torch
 sys.path.insert(0, ".")

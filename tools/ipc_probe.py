@@ -2,7 +2,6 @@
 write it over NVLink from a plain kernel, and how do a direct peer copy and NCCL all_to_all_single compare on the
 sequence-parallel exchange sizes?   torchrun --nproc-per-node 2 tools/ipc_probe.py"""
 import os
-import time
 
 import torch
 import torch.distributed as dist

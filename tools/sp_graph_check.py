@@ -2,7 +2,6 @@
 Run: timeout 150 python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/sp_graph_check.py"""
 import os
 import sys
-import time
 import torch
 import torch.distributed as dist
 sys.path.insert(0, ".")
