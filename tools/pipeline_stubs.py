@@ -80,14 +80,19 @@ def write_cond_image(path, height, width):
     Image.fromarray(img).save(path)
 
 
-def case():
-    """17 frames @ 64x64 (5 latent frames), 9-frame windows (3 latent frames) with overlap 2 -> windows [0,3) [1,4) [2,5);
-    2 steps, so the overlap blend (steps > 0, windows > 0) is exercised."""
+def case(name="windows3"):
+    """17 frames @ 64x64 (5 latent frames), 2 steps so that the overlap blend (step > 0, window > 0) is exercised.
+    "windows3": 9-frame windows (3 latent frames), overlap 2, uniform blend -> windows [0,3) [1,4) [2,5).
+    "short_last": 13-frame windows (4 latent frames), overlap 2, log blend -> windows [0,4) [2,5): the last window holds
+    only 3 latent frames, so the DiT sees zero-padded but live tokens and the audio runs to the end (SURVEY fact #9)."""
     fps, sr, frames = 25, 16000, 17
     n = frames * (sr // fps)
     t = torch.arange(n, dtype=torch.float32) / sr
     audio = 0.4 * torch.sin(2 * np.pi * 220 * t) + 0.2 * torch.sin(2 * np.pi * 523 * t + 1.0) * torch.cos(2 * np.pi * 3 * t)
     lat = synth.det_normal("pipe_case_latents", (1, 16, 5, 8, 8)).bfloat16().float()
-    return dict(height=64, width=64, clip_length=9, steps=2, fps=fps, sr=sr, audio=audio, latents=lat, overlap=2,
-                prompt="a person is talking", negative_prompt="blurry", text_scale=3.0,
-                audio_scale=5.0, cond_path=str(Path(tempfile.gettempdir()) / "sa_b200_cond_image.png"))
+    c = dict(height=64, width=64, clip_length=9, steps=2, fps=fps, sr=sr, audio=audio, latents=lat, overlap=2, scheme="uniform",
+             prompt="a person is talking", negative_prompt="blurry", text_scale=3.0,
+             audio_scale=5.0, cond_path=str(Path(tempfile.gettempdir()) / "sa_b200_cond_image.png"))
+    if name == "short_last":
+        c.update(clip_length=13, scheme="log", text_scale=2.0, audio_scale=4.0)
+    return c
