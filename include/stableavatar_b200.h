@@ -181,9 +181,28 @@ int sa_gather_rows_f32(const void* src, const void* idx, void* out, int32_t rows
  * 0-dim fp32 (sigma_next - sigma) times the bf16 prediction is a bf16 tensor under torch type promotion)
  * (pipe.py:754). noise_out (optional) receives the combined prediction.
  * dsigma_dev (optional, device float): when non-NULL it replaces dsigma, so a captured CUDA graph of the step can be
- * replayed with a new schedule value. */
+ * replayed with a new schedule value.
+ * latents_dtype: SA_BF16, or SA_F32 for a caller-supplied fp32 sample (the reference keeps the caller's dtype for the
+ * first step's `sample.float()`, pipe.py:393-396); out is always bf16 = model_output.dtype. */
 int sa_cfg_euler_step(const void* pred, const void* latents, void* out, void* noise_out, int64_t n, float audio_scale,
-                      float text_scale, float dsigma, const void* dsigma_dev, int32_t cfg, sa_stream_t stream);
+                      float text_scale, float dsigma, const void* dsigma_dev, int32_t cfg, int32_t latents_dtype,
+                      sa_stream_t stream);
+
+/* ---- sliding-window write-back with the overlap blend (wan/pipeline/wan_inference_long_pipeline.py:756-779) --------
+ * All windows of one denoise step in one launch, in window order: for window k (frames[k] latent frames starting at
+ * latent frame start[k], previous window ending at prev_end[k]) with blend[k] != 0 the first `overlap` frames become
+ * new * w_j + pred_latents[(prev_end - overlap + j) % N] * (1 - w_j) — rounded like the reference's bf16 tensor ops —
+ * then every frame is written to pred_latents[(start + i) % N]. new_latents: bf16 [n_windows, C, f_max, HW];
+ * pred_latents: [C, N, HW] bf16 or f32 (pred_dtype), zero-initialised by the caller; weight / one_minus_weight: the
+ * bf16-rounded values of the reference's weight tensor and of (1 - weight). */
+typedef struct {
+  const void* new_latents;
+  void* pred_latents;
+  int32_t n_windows, C, N, HW, f_max, overlap, pred_dtype;
+  int32_t start[64], frames[64], prev_end[64], blend[64];
+  float weight[64], one_minus_weight[64];
+} sa_window_blend_args;
+int sa_window_blend(const sa_window_blend_args* args, sa_stream_t stream);
 
 /* ---- Wan VAE decode (wan/models/wan_vae.py) --------------------------------------------------------------------
  * Activations are channels-last bf16 [T, H, W, C] (the reference is NCTHW fp32; layout and compute dtype are internal
@@ -235,12 +254,14 @@ int sa_vae_latent_in(const void* z, const void* wc, const void* bc, const void* 
  * Ulysses all-to-all of the DiT self-attention as direct peer stores: the caller maps every rank's receive buffers
  * (CUDA IPC) and passes the P base pointers. Head split: hg head groups x qs = P / hg query splits, rank = g * qs + s.
  *   sa_sp_scatter_qkv: src = local q|k|v rows [B, Ll, 3, heads, 128] bf16 (row stride ld elements) ->
- *       dst_a[r] = rank r's kv_recv [P, Ll, B, 2, heads/hg, 128] (slot = this rank) for the qs ranks of each head group,
- *       dst_b[r] = rank r's q_recv [hg, Ll, B, heads/hg, 128] (slot = this rank / qs) for the rank with s == this rank % qs.
- *   sa_sp_scatter_o: src = attention output [hg, Ll, B, heads/hg, 128] (source ranks i * qs + s) ->
+ *       dst_a[r] = rank r's kv_recv [B, P, Ll, 2, heads/hg, 128] (slot = this rank) for the qs ranks of each head group,
+ *       dst_b[r] = rank r's q_recv [B, hg, Ll, heads/hg, 128] (slot = this rank / qs) for the rank with s == this rank % qs.
+ *   sa_sp_scatter_o: src = attention output [B, hg, Ll, heads/hg, 128] (source ranks i * qs + s) ->
  *       dst_a[r] = rank r's o_recv [B, Ll, heads, 128], head columns of this rank's group.
  *   sa_sp_barrier: sig[r] = rank r's flag array (uint32 [P], zero-initialised), epoch = local uint32 counter. Orders all
- *       earlier stores of this stream before, and all peers' earlier stores after; traps after a bounded spin.
+ *       earlier stores of this stream before, and all peers' earlier stores after. The spin is bounded (default 10 min,
+ *       sa_sp_set_barrier_timeout_ms; 0 = unbounded like NCCL): on expiry the kernel prints the missing rank and traps,
+ *       which leaves a sticky context error — ranks must enter every forward within the timeout of each other.
  * No launch is issued on a peer's device; the kernels only store through the mapped pointers. */
 typedef struct {
   const void* src;
@@ -248,10 +269,12 @@ typedef struct {
   void* dst_b[8];
   int64_t ld;
   int32_t B, Ll, heads, head_dim, P, rank, hg;
+  int32_t b_first, b_count; /* CFG samples [b_first, b_first + b_count) handled by this launch; b_count 0 = up to B */
 } sa_sp_args;
 int sa_sp_scatter_qkv(const sa_sp_args* args, sa_stream_t stream);
 int sa_sp_scatter_o(const sa_sp_args* args, sa_stream_t stream);
 int sa_sp_barrier(void* const* sig, void* epoch, int32_t P, int32_t rank, sa_stream_t stream);
+int sa_sp_set_barrier_timeout_ms(int64_t ms);
 /* Producer fusion of sa_rmsnorm_rope + sa_sp_scatter_qkv: q and k of the fused QKV rows (args->src, un-normalised) get the
  * WanRMSNorm + 3-D RoPE of 1B.py:296-342 (token index = tok_offset + row % Ll, same arithmetic and rounding as
  * sa_rmsnorm_rope), v is copied, and every chunk goes straight to its destination rank's kv_recv / q_recv (layouts as

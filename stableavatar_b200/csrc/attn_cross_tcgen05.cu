@@ -493,12 +493,7 @@ extern "C" int sa_cross_attn3_d128(const sa_cross_attn_args* a, sa_stream_t stre
     if ((rc = mk(&tk[s], cs->k, cs->k_ls, cs->k_bs))) return rc;
     if ((rc = mk(&tv[s], cs->v, cs->v_ls, cs->v_bs))) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cross_attn_kernel)");
-    attr_set = true;
-  }
+  if (int rc2 = ensure_dyn_smem(cross_attn_kernel, SMEM_BYTES, "cross_attn_kernel")) return rc2;
   dim3 grid((a->q_len + BQ - 1) / BQ, a->heads, a->batch);
   cross_attn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk[0], tv[0], tk[1], tv[1], tk[2], tv[2], p);
   cudaError_t e = cudaGetLastError();

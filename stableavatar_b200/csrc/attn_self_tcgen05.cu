@@ -1,9 +1,7 @@
-// attn_v8_tcgen05.cu — flash attention forward, head_dim 128, non-causal, for sm_100a: decoupled pipeline (as
-// attn_v4_tcgen05.cu) with one MMA-issuing warp per Q tile. DEFAULT kernel behind sa_flash_attn_d128.
+// attn_self_tcgen05.cu — flash attention forward, head_dim 128, non-causal, for sm_100a. The one kernel behind
+// sa_flash_attn_d128 (earlier generations live as text under profiles/experiments/ with what each one taught).
 //
-// The first kernel (attn_tcgen05.cu) keeps P in the TMEM columns of S, so S(j+1) cannot be issued before P(j)V has
-// consumed P(j): softmax and tensor pipe take turns (profiles/r01_attn_v2.md: softmax warps wait 48 % of the time,
-// tensor pipe 56 % active). Here the two are decoupled:
+// Softmax and tensor pipe are decoupled:
 //
 //   * Q lives in TMEM (64 columns per 128-row tile, stored once by the softmax threads) and S = Q K^T is a TS-mode MMA
 //     (A from TMEM) — which also halves the shared-memory operand traffic of the score MMAs;
@@ -17,11 +15,13 @@
 // {K, V} 64-key tiles. TMEM columns: Q0 0-63, Q1 64-127, S0 128-191, S1 192-255, O0 256-383, O1 384-511.
 // Warps: 0-3 softmax tile 0, 4-7 softmax tile 1 (TMEM lane quarter = warp % 4), 8 = TMA producer, 9 / 10 = MMA issuer
 // of Q tile 0 / 1 (a single issuer serving both tiles in a fixed order parks on the other tile's P: +4 % from the split).
-// Softmax arithmetic is the one of attn_tcgen05.cu (lazy rescale, FMNMX3, FFMA2, optional FMA-pipe exp2).
+// Softmax arithmetic: lazy rescale of O / l (only when the row max grew by more than 2^8), FMNMX3 row max, FFMA2 scale,
+// MUFU.EX2 exponentials staged back to back (16/clk/SM: the XU pipe is the co-limiter, tools/micro/mufu_bench.cu).
 //
 // Replaces attention() of the reference (wan/models/wan_fantasy_transformer3d_1B.py:158-207, SDPA branch).
 #include <stdlib.h>
 
+#include <mutex>
 #include <type_traits>
 
 #include "../../include/stableavatar_b200.h"
@@ -51,7 +51,6 @@ struct Params {
   int accumulate;
 };
 
-template <int kPolyPairs>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -272,80 +271,40 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
       const float nmc = -m_ref * c;
       const uint64_t nmc2 = pack_f32x2(nmc, nmc);
       uint8_t* p_row = p_row0 + (u & 1) * P_BYTES;
-      if constexpr (kPolyPairs == 0) {
-        // Staged so that no instruction waits on its predecessor: (A) 32 independent packed scales, (B) 64 MUFU.EX2
-        // back to back (the XU pipe, 8 cycles per warp instruction, is the only limiter of this stage and the other
-        // softmax warp of the sub-partition fills the issue slots), (C) row sums on 4 chains + bf16 packing + stores.
-        uint64_t x2[32];
+      {
+      // Staged so that no instruction waits on its predecessor: (A) 32 independent packed scales, (B) 64 MUFU.EX2
+      // back to back (the XU pipe, 8 cycles per warp instruction, is the only limiter of this stage and the other
+      // softmax warp of the sub-partition fills the issue slots), (C) row sums on 4 chains + bf16 packing + stores.
+      uint64_t x2[32];
 #pragma unroll
-        for (int t = 0; t < 32; ++t)
-          x2[t] = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), c2, nmc2);
-        float pe[64];
+      for (int t = 0; t < 32; ++t)
+        x2[t] = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), c2, nmc2);
+      float pe[64];
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          float x0, x1;
-          unpack_f32x2(x2[t], x0, x1);
-          pe[2 * t] = ex2_approx(x0);
-          pe[2 * t + 1] = ex2_approx(x1);
-        }
-        uint64_t la = lsum2, lb = lsum2b, lc = pack_f32x2(0.f, 0.f), ld = pack_f32x2(0.f, 0.f);
+      for (int t = 0; t < 32; ++t) {
+        float x0, x1;
+        unpack_f32x2(x2[t], x0, x1);
+        pe[2 * t] = ex2_approx(x0);
+        pe[2 * t + 1] = ex2_approx(x1);
+      }
+      uint64_t la = lsum2, lb = lsum2b, lc = pack_f32x2(0.f, 0.f), ld = pack_f32x2(0.f, 0.f);
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int t4 = 0; t4 < 4; ++t4) {
-            const int t = c8 * 4 + t4;
-            const uint64_t p2 = pack_f32x2(pe[2 * t], pe[2 * t + 1]);
-            if (t4 == 0) la = add_f32x2(la, p2);
-            else if (t4 == 1) lb = add_f32x2(lb, p2);
-            else if (t4 == 2) lc = add_f32x2(lc, p2);
-            else ld = add_f32x2(ld, p2);
-            pk[t4] = pack_bf16x2(pe[2 * t], pe[2 * t + 1]);
-          }
-          *reinterpret_cast<uint4*>(p_row + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
-        lsum2 = add_f32x2(la, lc);
-        lsum2b = add_f32x2(lb, ld);
-      } else {
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {   // 8 chunks of 8 keys = 16 bytes of bf16
+      for (int c8 = 0; c8 < 8; ++c8) {
         uint32_t pk[4];
 #pragma unroll
         for (int t4 = 0; t4 < 4; ++t4) {
-          const int t = c8 * 4 + t4;     // column pair index
-          const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), c2, nmc2);
-          uint64_t p2;
-          if ((t & 7) < kPolyPairs) {
-            float x0, x1;
-            unpack_f32x2(x2, x0, x1);
-            x0 = fmaxf(x0, -126.0f);
-            x1 = fmaxf(x1, -126.0f);
-            const uint64_t xc = pack_f32x2(x0, x1);
-            const uint64_t xi = add_f32x2(xc, pack_f32x2(12582912.0f, 12582912.0f));
-            const uint64_t xr = add_f32x2(xi, pack_f32x2(-12582912.0f, -12582912.0f));
-            const uint64_t f = fma_f32x2(xr, pack_f32x2(-1.0f, -1.0f), xc);
-            uint64_t q = fma_f32x2(f, pack_f32x2(0.05550411f, 0.05550411f), pack_f32x2(0.24022651f, 0.24022651f));
-            q = fma_f32x2(q, f, pack_f32x2(0.69314718f, 0.69314718f));
-            q = fma_f32x2(q, f, pack_f32x2(1.0f, 1.0f));
-            float q0_, q1_, i0, i1;
-            unpack_f32x2(q, q0_, q1_);
-            unpack_f32x2(xi, i0, i1);
-            q0_ = __uint_as_float(__float_as_uint(q0_) + (__float_as_uint(i0) << 23));
-            q1_ = __uint_as_float(__float_as_uint(q1_) + (__float_as_uint(i1) << 23));
-            p2 = pack_f32x2(q0_, q1_);
-            pk[t4] = pack_bf16x2(q0_, q1_);
-          } else {
-            float x0, x1;
-            unpack_f32x2(x2, x0, x1);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-            p2 = pack_f32x2(p0, p1);
-            pk[t4] = pack_bf16x2(p0, p1);
-          }
-          if (t4 & 1) lsum2b = add_f32x2(lsum2b, p2);
-          else lsum2 = add_f32x2(lsum2, p2);
+          const int t = c8 * 4 + t4;
+          const uint64_t p2 = pack_f32x2(pe[2 * t], pe[2 * t + 1]);
+          if (t4 == 0) la = add_f32x2(la, p2);
+          else if (t4 == 1) lb = add_f32x2(lb, p2);
+          else if (t4 == 2) lc = add_f32x2(lc, p2);
+          else ld = add_f32x2(ld, p2);
+          pk[t4] = pack_bf16x2(pe[2 * t], pe[2 * t + 1]);
         }
         *reinterpret_cast<uint4*>(p_row + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
+      lsum2 = add_f32x2(la, lc);
+      lsum2b = add_f32x2(lb, ld);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -410,10 +369,20 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
 }  // namespace attn8
 }  // namespace sa
 
-// Called by sa_flash_attn_d128 (attn_tcgen05.cu) when the decoupled kernel is selected.
-int sa_flash_attn_d128_v8(const sa_attn_args* a, int poly, cudaStream_t stream) {
+extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
   using namespace sa;
   using namespace sa::attn8;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->q || !a->k || !a->v || !a->out) { set_error("sa_flash_attn_d128: null pointer"); return SA_ERR_BAD_ARG; }
+  if (a->batch <= 0 || a->heads <= 0 || a->q_len <= 0 || a->kv_len <= 0) {
+    set_error("sa_flash_attn_d128: non-positive dims");
+    return SA_ERR_BAD_ARG;
+  }
+  if (a->q_ls % 8 || a->k_ls % 8 || a->v_ls % 8 || a->o_ls % 8 || a->q_bs % 8 || a->k_bs % 8 || a->v_bs % 8 ||
+      a->o_bs % 8) {
+    set_error("sa_flash_attn_d128: strides must be multiples of 8 elements");
+    return SA_ERR_BAD_ARG;
+  }
   CUtensorMap tk, tv;
   auto mk = [&](CUtensorMap* m, const void* base, int len, long long ls, long long bs) {
     uint64_t dims[4] = {(uint64_t)D, (uint64_t)len, (uint64_t)a->heads, (uint64_t)a->batch};
@@ -432,23 +401,9 @@ int sa_flash_attn_d128_v8(const sa_attn_args* a, int poly, cudaStream_t stream) 
   p.q_len = a->q_len; p.kv_len = a->kv_len;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaSuccess;
-    auto set = [&](auto* k) { if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); };
-    set(flash_attn_v8_kernel<0>); set(flash_attn_v8_kernel<1>); set(flash_attn_v8_kernel<2>);
-    set(flash_attn_v8_kernel<3>); set(flash_attn_v8_kernel<4>);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(flash_attn_v8_kernel)");
-    attr_set = true;
-  }
+  if ((rc = ensure_dyn_smem(flash_attn_v8_kernel, SMEM_BYTES, "flash_attn_v8_kernel"))) return rc;
   dim3 grid((a->q_len + 2 * BQ - 1) / (2 * BQ), a->heads, a->batch);
-  switch (poly) {
-    case 0: flash_attn_v8_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p); break;
-    case 1: flash_attn_v8_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p); break;
-    case 3: flash_attn_v8_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p); break;
-    case 4: flash_attn_v8_kernel<4><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p); break;
-    default: flash_attn_v8_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p); break;
-  }
+  flash_attn_v8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "flash_attn_v8_kernel launch");
   return SA_OK;

@@ -171,12 +171,7 @@ extern "C" int sa_attn_small_q(const sa_attn_args* a, int32_t head_dim, sa_strea
   p.q_bs = a->q_bs; p.q_ls = a->q_ls; p.k_bs = a->k_bs; p.k_ls = a->k_ls;
   p.v_bs = a->v_bs; p.v_ls = a->v_ls; p.o_bs = a->o_bs; p.o_ls = a->o_ls;
   p.heads = a->heads; p.q_len = a->q_len; p.kv_len = a->kv_len; p.d = head_dim; p.tk = tk; p.scale = a->scale;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_small_kernel)");
-    attr = true;
-  }
+  if (int rc = ensure_dyn_smem(attn_small_kernel, 200 * 1024, "attn_small_kernel")) return rc;
   attn_small_kernel<<<a->batch * a->heads, THREADS, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "attn_small_kernel launch");

@@ -295,12 +295,7 @@ extern "C" int sa_conv3d_cl(const sa_conv_args* a, sa_stream_t stream_) {
     int rc = make_tmap_bf16(&tw, a->w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv3d_kernel)");
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(conv3d_kernel, SMEM_BYTES, "conv3d_kernel")) return rc;
   const int tiles = p.tiles_n * p.Tout * p.tiles_w * p.tiles_h;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   conv3d_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tin, tw, p);

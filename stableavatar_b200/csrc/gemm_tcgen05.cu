@@ -354,13 +354,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 template <bool FAST, int ACT, int RES>
 static int launch(const CUtensorMap& tma, const CUtensorMap& tmb, const CUtensorMap& tmc, const Params& p, int grid,
                   cudaStream_t stream) {
-  static bool attr_set = false;
   auto* kern = gemm_bf16_kernel<FAST, ACT, RES>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_bf16_kernel)");
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(kern, SMEM_BYTES, "gemm_bf16_kernel")) return rc;
   kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tma, tmb, tmc, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "gemm_bf16_kernel launch");

@@ -128,7 +128,8 @@ __global__ void gather_rows_kernel(const float* src, const int* idx, float* out,
 // ------------------------------------------------------------------------------------------------ CFG + Euler
 // noise = uncond + a*(drop_audio - uncond) + t*(cond - drop_audio)   every op a bf16 tensor op (pipe.py:752-753)
 // latents = bf16(float(latents) + bf16(dsigma * noise))             (diffusers FlowMatchEulerDiscreteScheduler.step)
-__global__ void cfg_euler_kernel(const __nv_bfloat16* pred, const __nv_bfloat16* lat, __nv_bfloat16* out,
+template <typename LatT>
+__global__ void cfg_euler_kernel(const __nv_bfloat16* pred, const LatT* lat, __nv_bfloat16* out,
                                  __nv_bfloat16* noise_out, long long n, float audio_scale, float text_scale,
                                  float dsigma, const float* dsigma_dev, int cfg) {
   if (dsigma_dev) dsigma = *dsigma_dev;   // schedule value kept on the device so that a captured CUDA graph can be replayed
@@ -147,7 +148,53 @@ __global__ void cfg_euler_kernel(const __nv_bfloat16* pred, const __nv_bfloat16*
     // (sigma_next - sigma) is a 0-dim fp32 tensor: its product with the bf16 prediction is a bf16 tensor (type
     // promotion ignores 0-dim operands of the same category); the add with the fp32 sample is fp32; no FMA contraction.
     const float step = bf16_round(__fmul_rn(dsigma, np));
-    out[i] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(lat[i]), step));
+    out[i] = __float2bfloat16_rn(__fadd_rn(static_cast<float>(lat[i]), step));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ window blend (K16)
+// All windows of one denoise step written back into pred_latents with the overlap blend, in window order, in ONE
+// launch (pipe.py:756-779). Everything is elementwise over (channel, h, w) and the frame bookkeeping is static, so a
+// thread owns one (channel, pixel) column and walks windows and frames sequentially, reproducing statement by statement:
+//     latents[:, :, s_j] = latents[:, :, s_j] * w_j + pred_latents[:, :, e_j] * (1 - w_j)     s_j = j % f, e_j = (prev_end - n + j) % N
+//     latents = latents.to(bf16); pred_latents[:, :, (ws + i) % N] = latents[:, :, i]
+// with torch's roundings: latents and the weights are bf16, so every product / sum of bf16 tensors is rounded to bf16;
+// with an fp32 pred_latents (caller-supplied fp32 noise) the second product and the sum are fp32.
+constexpr int BLEND_MAX_WINDOWS = 64, BLEND_MAX_OVERLAP = 64;
+struct WindowBlendParams {
+  const __nv_bfloat16* new_lat;   // [W, C, f_max, HW]: window k's f[k] frames first
+  void* pred;                     // [C, N, HW] bf16 or f32, zero-initialised by the caller
+  int W, C, N, HW, f_max, overlap, pred_f32;
+  int ws[BLEND_MAX_WINDOWS], f[BLEND_MAX_WINDOWS], prev_end[BLEND_MAX_WINDOWS], blend[BLEND_MAX_WINDOWS];
+  float w[BLEND_MAX_OVERLAP], omw[BLEND_MAX_OVERLAP];   // bf16 values of w_j and of the bf16 tensor (1 - w)_j
+};
+
+template <typename PredT>
+__global__ void window_blend_kernel(const __grid_constant__ WindowBlendParams p) {
+  PredT* pred = reinterpret_cast<PredT*>(p.pred);
+  const long long total = (long long)p.C * p.HW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = idx / p.HW, x = idx % p.HW;
+    PredT* pc = pred + (long long)c * p.N * p.HW + x;
+    for (int k = 0; k < p.W; ++k) {
+      const __nv_bfloat16* nw = p.new_lat + (((long long)k * p.C + c) * p.f_max) * p.HW + x;
+      const int f = p.f[k];
+      float tmp[BLEND_MAX_OVERLAP];
+      if (p.blend[k]) {                                   // right-hand sides from the values before any assignment
+        for (int j = 0; j < p.overlap; ++j) {
+          const int e = ((p.prev_end[k] - p.overlap + j) % p.N + p.N) % p.N;
+          const float a = bf16_round(__fmul_rn(__bfloat162float(nw[(long long)(j % f) * p.HW]), p.w[j]));
+          const float pe = static_cast<float>(pc[(long long)e * p.HW]);
+          const float b = sizeof(PredT) == 4 ? __fmul_rn(pe, p.omw[j]) : bf16_round(__fmul_rn(pe, p.omw[j]));
+          tmp[j] = bf16_round(__fadd_rn(a, b));
+        }
+      }
+      for (int i = 0; i < f; ++i) {
+        float v = __bfloat162float(nw[(long long)i * p.HW]);
+        if (p.blend[k] && i < p.overlap) v = tmp[i + f * ((p.overlap - 1 - i) / f)];   // the last j with j % f == i wins
+        pc[(long long)((p.ws[k] + i) % p.N) * p.HW] = static_cast<PredT>(v);
+      }
+    }
   }
 }
 
@@ -205,12 +252,7 @@ extern "C" int sa_small_linear_f32(const void* x, const void* w, const void* bia
   misc::SmallLinParams p{reinterpret_cast<const float*>(x), w, bias, reinterpret_cast<float*>(out_f32),
                          reinterpret_cast<__nv_bfloat16*>(out_bf16), M, N, K, pre, w_dtype};
   const size_t smem = (size_t)M * K * 4;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(misc::small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(small_linear_kernel)");
-    attr = true;
-  }
+  if (int rc = ensure_dyn_smem(misc::small_linear_kernel, 96 * 1024, "small_linear_kernel")) return rc;
   misc::small_linear_kernel<<<(N + 7) / 8, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   SA_LAUNCH_CHECK("small_linear_kernel launch");
   return SA_OK;
@@ -227,13 +269,49 @@ extern "C" int sa_gather_rows_f32(const void* src, const void* idx, void* out, i
 
 extern "C" int sa_cfg_euler_step(const void* pred, const void* latents, void* out, void* noise_out, int64_t n,
                                  float audio_scale, float text_scale, float dsigma, const void* dsigma_dev, int32_t cfg,
-                                 sa_stream_t stream) {
+                                 int32_t latents_dtype, sa_stream_t stream) {
   using namespace sa;
-  if (!pred || !latents || !out || n <= 0) { set_error("sa_cfg_euler_step: bad argument"); return SA_ERR_BAD_ARG; }
-  misc::cfg_euler_kernel<<<misc::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(pred), reinterpret_cast<const __nv_bfloat16*>(latents),
-      reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<__nv_bfloat16*>(noise_out), n, audio_scale, text_scale,
-      dsigma, reinterpret_cast<const float*>(dsigma_dev), cfg);
+  if (!pred || !latents || !out || n <= 0 || (latents_dtype != SA_BF16 && latents_dtype != SA_F32)) {
+    set_error("sa_cfg_euler_step: bad argument");
+    return SA_ERR_BAD_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  auto* pr = reinterpret_cast<const __nv_bfloat16*>(pred);
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  auto* no = reinterpret_cast<__nv_bfloat16*>(noise_out);
+  auto* ds = reinterpret_cast<const float*>(dsigma_dev);
+  if (latents_dtype == SA_F32)
+    misc::cfg_euler_kernel<float><<<misc::grid_for(n), 256, 0, st>>>(pr, reinterpret_cast<const float*>(latents), o, no, n,
+                                                                     audio_scale, text_scale, dsigma, ds, cfg);
+  else
+    misc::cfg_euler_kernel<__nv_bfloat16><<<misc::grid_for(n), 256, 0, st>>>(
+        pr, reinterpret_cast<const __nv_bfloat16*>(latents), o, no, n, audio_scale, text_scale, dsigma, ds, cfg);
   SA_LAUNCH_CHECK("cfg_euler_kernel launch");
+  return SA_OK;
+}
+
+extern "C" int sa_window_blend(const sa_window_blend_args* a, sa_stream_t stream) {
+  using namespace sa;
+  if (!a || !a->new_latents || !a->pred_latents || a->n_windows <= 0 || a->n_windows > misc::BLEND_MAX_WINDOWS || a->C <= 0 ||
+      a->N <= 0 || a->HW <= 0 || a->f_max <= 0 || a->overlap < 0 || a->overlap > misc::BLEND_MAX_OVERLAP ||
+      (a->pred_dtype != SA_BF16 && a->pred_dtype != SA_F32)) {
+    set_error("sa_window_blend: bad argument (<= %d windows, overlap <= %d)", misc::BLEND_MAX_WINDOWS, misc::BLEND_MAX_OVERLAP);
+    return SA_ERR_BAD_ARG;
+  }
+  misc::WindowBlendParams p;
+  p.new_lat = reinterpret_cast<const __nv_bfloat16*>(a->new_latents);
+  p.pred = a->pred_latents;
+  p.W = a->n_windows; p.C = a->C; p.N = a->N; p.HW = a->HW; p.f_max = a->f_max; p.overlap = a->overlap;
+  p.pred_f32 = a->pred_dtype == SA_F32;
+  for (int k = 0; k < p.W; ++k) {
+    if (a->frames[k] <= 0 || a->frames[k] > a->f_max) { set_error("sa_window_blend: window %d has %d frames", k, a->frames[k]); return SA_ERR_BAD_ARG; }
+    p.ws[k] = a->start[k]; p.f[k] = a->frames[k]; p.prev_end[k] = a->prev_end[k]; p.blend[k] = a->blend[k];
+  }
+  for (int j = 0; j < p.overlap; ++j) { p.w[j] = a->weight[j]; p.omw[j] = a->one_minus_weight[j]; }
+  const long long total = (long long)p.C * p.HW;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p.pred_f32) misc::window_blend_kernel<float><<<misc::grid_for(total), 256, 0, st>>>(p);
+  else misc::window_blend_kernel<__nv_bfloat16><<<misc::grid_for(total), 256, 0, st>>>(p);
+  SA_LAUNCH_CHECK("window_blend_kernel launch");
   return SA_OK;
 }

@@ -291,14 +291,16 @@ struct RmsScatterParams {
   long long ld;
   int rows, C, Ll, B, F, H, W, tok_offset;
   int nh, P, rank, qs, hp;
+  int b_first;               // first CFG sample of this launch (rows = b_count * Ll)
   float eps;
 };
 
 template <int NCH>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 8 ? 4 : 2) rmsnorm_rope_scatter_kernel(const RmsScatterParams p) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
+  const int row_l = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row_l >= p.rows) return;
+  const int row = p.b_first * p.Ll + row_l;
   const int which = blockIdx.y;  // 0 q, 1 k, 2 v
   const __nv_bfloat16* x = p.qkv + which * p.C;
   const int nchunks = p.C >> 3;
@@ -327,8 +329,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 8 ? 4 : 2) rmsnor
   const bool rotate = which < 2 && p.freqs != nullptr && tok < p.F * p.H * p.W;
   const int pf = tok / (p.H * p.W), ph = (tok / p.W) % p.H, pw = tok % p.W;
   const int s_me = p.rank % p.qs;
-  const long long q_row = ((long long)(p.rank / p.qs) * p.Ll + t_loc) * p.B + b;   // row index inside q_recv
-  const long long kv_row = ((long long)p.rank * p.Ll + t_loc) * p.B + b;           // row index inside kv_recv
+  const long long q_row = ((long long)b * (p.P / p.qs) + p.rank / p.qs) * p.Ll + t_loc;   // row index inside q_recv
+  const long long kv_row = ((long long)b * p.P + p.rank) * p.Ll + t_loc;                  // row index inside kv_recv
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int ch = lane + c * 32;
@@ -502,7 +504,10 @@ extern "C" int sa_sp_norm_rope_scatter(const sa_sp_args* a, const void* weight_q
     p.q_dst[r] = r < a->P ? reinterpret_cast<uint4*>(a->dst_b[r]) : nullptr;
     if (r < a->P && (!p.kv_dst[r] || !p.q_dst[r])) { set_error("sa_sp_norm_rope_scatter: null destination for rank %d", r); return SA_ERR_BAD_ARG; }
   }
-  p.ld = a->ld; p.rows = a->B * a->Ll; p.C = C; p.Ll = a->Ll; p.B = a->B; p.F = F; p.H = H; p.W = W; p.tok_offset = tok_offset;
+  const int b_count = a->b_count > 0 ? a->b_count : a->B - a->b_first;
+  if (a->b_first < 0 || a->b_first + b_count > a->B) { set_error("sa_sp_norm_rope_scatter: sample range outside the batch"); return SA_ERR_BAD_ARG; }
+  p.b_first = a->b_first;
+  p.ld = a->ld; p.rows = b_count * a->Ll; p.C = C; p.Ll = a->Ll; p.B = a->B; p.F = F; p.H = H; p.W = W; p.tok_offset = tok_offset;
   p.nh = a->heads; p.P = a->P; p.rank = a->rank; p.qs = a->P / a->hg; p.hp = a->heads / a->hg; p.eps = eps;
   dim3 grid((p.rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 3);
   const int nch = (C / 8 + 31) / 32;

@@ -6,6 +6,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "../../include/stableavatar_b200.h"
 
 namespace sa {
@@ -76,12 +80,31 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }
 
 int sm_count() {
+  static std::once_flag once;
   static int n = 0;
-  if (n) return n;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  std::call_once(once, [] {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  });
   return n;
+}
+
+int ensure_dyn_smem(const void* kernel, int bytes, const char* name) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({dev, kernel})) return SA_OK;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(%s, %d bytes): %s", name, bytes, cudaGetErrorName(e));
+    return SA_ERR_CUDA;
+  }
+  done.insert({dev, kernel});
+  return SA_OK;
 }
 
 }  // namespace sa

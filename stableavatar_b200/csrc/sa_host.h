@@ -24,4 +24,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 int sm_count();
 
+// Opt a kernel into `bytes` of dynamic shared memory on the CURRENT device, once per (device, kernel). Thread-safe:
+// the reference's app.py calls the pipeline from gradio worker threads.
+int ensure_dyn_smem(const void* kernel, int bytes, const char* name);
+template <class K>
+inline int ensure_dyn_smem(K* kernel, int bytes, const char* name) {
+  return ensure_dyn_smem(reinterpret_cast<const void*>(kernel), bytes, name);
+}
+
 }  // namespace sa

@@ -10,18 +10,25 @@
 //
 // Head / token split (sequence_parallel.plan): hg = gcd(heads, P) head groups x qs = P / hg query splits; rank
 // r = g * qs + s owns head group g (hp = heads / hg heads) and the query tokens of the source ranks r' with r' % qs == s.
-//   kv_recv on rank r : [P (source rank), Ll, B, 2 (k, v), hp, d]
-//   q_recv  on rank r : [P / qs (source ranks r' % qs == s, ascending), Ll, B, hp, d]
+//   kv_recv on rank r : [B, P (source rank), Ll, 2 (k, v), hp, d]   = K / V of [B, L, hp, d] with token stride 2*hp*d
+//   q_recv  on rank r : [B, P / qs (source ranks r' % qs == s, ascending), Ll, hp, d]
 //   o_recv  on rank r : [B, Ll, heads, d]   — the layout the output projection reads, every head group filled by its owner
+// The batch (CFG sample) index is outermost everywhere, and every entry point takes a sample range [b_first, b_first +
+// b_count): the host pipelines the exchange of sample b + 1 under the attention of sample b (sequence_parallel.py).
 #include "../../include/stableavatar_b200.h"
 #include "sa_host.h"
 #include "sa_ptx.cuh"
 #include <string.h>
 
+#include <atomic>
+
 namespace sa {
 namespace sp {
 
 constexpr int MAX_RANKS = 8;
+// Spin bound of sa_sp_barrier. Default 10 min: long enough for host-side skew between ranks (one rank writing a video,
+// a graph capture, GC), short enough that a dead peer does not hang the GPU for ever. 0 = unbounded. sa_sp_set_barrier_timeout_ms.
+static std::atomic<uint64_t> g_barrier_timeout_ns{600ull * 1000000000ull};
 constexpr int THREADS = 192;  // 3 * 12 heads * 16 chunks = 576 = 3 x 192 columns per token for the 1.3B model
 
 struct ScatterParams {
@@ -30,6 +37,7 @@ struct ScatterParams {
   uint4* dst_b[MAX_RANKS];  // qkv: q_recv bases
   long long ld8;            // source row stride in 16-byte chunks
   int B, Ll, nh, P, rank, hg, qs, hp, n_src;
+  int b_first, b_count;     // CFG samples handled by this launch
 };
 
 // d = 128 -> 16 chunks of 16 bytes per head. A thread owns ONE 16-byte column e of the token row [3, nh, 16] (its
@@ -43,11 +51,11 @@ __global__ void __launch_bounds__(THREADS) scatter_qkv_kernel(const ScatterParam
   const int c = e & 15, h = (e >> 4) % p.nh, which = (e >> 4) / p.nh;  // which: 0 q, 1 k, 2 v
   const int g = h / p.hp, hl = h % p.hp;
   const int s_me = p.rank % p.qs;
-  const int n_tok = p.B * p.Ll;
+  const int n_tok = p.b_count * p.Ll;
   // four tokens per iteration: the loads are issued before the (possibly aliasing, as far as the compiler knows) stores
   constexpr int U = 4;
   const bool is_q = which == 0;
-  const long long slot = is_q ? (long long)(p.rank / p.qs) * p.Ll : (long long)p.rank * p.Ll;
+  const int n_slots = is_q ? p.n_src : p.P, slot = is_q ? p.rank / p.qs : p.rank;
   const int row_chunks = is_q ? p.hp * 16 : 2 * p.hp * 16;
   const int inner = is_q ? hl * 16 + c : ((which - 1) * p.hp + hl) * 16 + c;
   uint4* const q_dst = p.dst_b[g * p.qs + s_me];
@@ -56,14 +64,14 @@ __global__ void __launch_bounds__(THREADS) scatter_qkv_kernel(const ScatterParam
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int bt = bt0 + u * gridDim.x;
-      if (bt < n_tok) val[u] = __ldg(p.src + (long long)bt * p.ld8 + e);
+      if (bt < n_tok) val[u] = __ldg(p.src + ((long long)p.b_first * p.Ll + bt) * p.ld8 + e);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int bt = bt0 + u * gridDim.x;
       if (bt >= n_tok) continue;
-      const int t = bt % p.Ll, b = bt / p.Ll;
-      const long long off = ((slot + t) * p.B + b) * row_chunks + inner;
+      const int t = bt % p.Ll, b = p.b_first + bt / p.Ll;
+      const long long off = (((long long)b * n_slots + slot) * p.Ll + t) * row_chunks + inner;
       if (is_q) {
         q_dst[off] = val[u];
       } else {
@@ -73,18 +81,21 @@ __global__ void __launch_bounds__(THREADS) scatter_qkv_kernel(const ScatterParam
   }
 }
 
-// src: attention output [n_src, Ll, B, hp, 16 chunks] of head group g for the query tokens of source ranks
-// i * qs + s_me; chunk goes to rank i * qs + s_me at [b, t, g * hp + hl, c]. blockDim.x = rows_per_block * hp * 16.
-__global__ void __launch_bounds__(THREADS) scatter_o_kernel(const ScatterParams p, int rows_per_block) {
+// src: attention output [B, n_src, Ll, hp, 16 chunks] of head group g for the query tokens of source ranks
+// i * qs + s_me; chunk goes to rank i * qs + s_me at [b, t, g * hp + hl, c]. One 16-byte chunk per thread and iteration,
+// any hp (14B at P = 2: 20 heads per rank).
+__global__ void __launch_bounds__(256) scatter_o_kernel(const ScatterParams p) {
   const int cols = p.hp * 16;
-  const int col = threadIdx.x % cols, rsub = threadIdx.x / cols;
   const int s_me = p.rank % p.qs, g = p.rank / p.qs;
-  const int n_rows = p.n_src * p.Ll * p.B;
-  const int inner = g * cols + col;                      // (g * hp + hl) * 16 + c
-  for (int row = blockIdx.x * rows_per_block + rsub; row < n_rows; row += gridDim.x * rows_per_block) {
-    const int b = row % p.B, lt = row / p.B;
-    const int t = lt % p.Ll, src = lt / p.Ll;
-    p.dst_a[src * p.qs + s_me][((long long)b * p.Ll + t) * (p.nh * 16) + inner] = p.src[(long long)row * cols + col];
+  const unsigned rows_b = (unsigned)p.n_src * p.Ll;                 // rows per sample
+  const unsigned total = (unsigned)p.b_count * rows_b * cols;      // < 2^31, checked by the host
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned row = idx / cols, col = idx - row * cols;
+    const unsigned bl = row / rows_b, lt = row - bl * rows_b;
+    const unsigned src = lt / p.Ll, t = lt - src * p.Ll;
+    const int b = p.b_first + bl;
+    p.dst_a[src * p.qs + s_me][((long long)b * p.Ll + t) * (p.nh * 16) + g * cols + col] =
+        __ldg(p.src + ((long long)b * rows_b + lt) * cols + col);
   }
 }
 
@@ -92,6 +103,7 @@ struct BarrierParams {
   uint32_t* sig[MAX_RANKS];  // sig[r]: rank r's flag array [P] (peer mapping; sig[rank] is local)
   uint32_t* epoch;           // local device counter: number of barriers passed so far
   int P, rank;
+  uint64_t timeout_ns;       // 0 = wait for ever (what NCCL does)
 };
 
 // One block, one thread per rank. All stores issued by earlier kernels of this stream (the scatters) are ordered before
@@ -112,7 +124,7 @@ __global__ void barrier_kernel(const BarrierParams p) {
     for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if ((int32_t)(v - e) >= 0) break;
-      if (((++spins) & 0xff) == 0 && globaltimer_ns() - t0 > 4 * SA_WAIT_TIMEOUT_NS) {
+      if (((++spins) & 0xff) == 0 && p.timeout_ns && globaltimer_ns() - t0 > p.timeout_ns) {
         printf("sa_sp_barrier: rank %d timed out waiting for rank %d (epoch %u, saw %u)\n", p.rank, r, e, v);
         __trap();
       }
@@ -133,6 +145,9 @@ static int fill(ScatterParams& p, const sa_sp_args* a, const char* who) {
   p.B = a->B; p.Ll = a->Ll; p.nh = a->heads; p.P = a->P; p.rank = a->rank; p.hg = a->hg; p.qs = a->P / a->hg;
   p.hp = a->heads / a->hg; p.n_src = a->P / p.qs;
   p.ld8 = a->ld / 8;
+  p.b_first = a->b_first;
+  p.b_count = a->b_count > 0 ? a->b_count : a->B - a->b_first;
+  if (p.b_first < 0 || p.b_first + p.b_count > a->B) { set_error("%s: sample range [%d, %d) outside batch %d", who, p.b_first, p.b_first + p.b_count, a->B); return SA_ERR_BAD_ARG; }
   for (int r = 0; r < MAX_RANKS; ++r) {
     p.dst_a[r] = r < a->P ? reinterpret_cast<uint4*>(a->dst_a[r]) : nullptr;
     p.dst_b[r] = r < a->P ? reinterpret_cast<uint4*>(a->dst_b[r]) : nullptr;
@@ -154,7 +169,7 @@ extern "C" int sa_sp_scatter_qkv(const sa_sp_args* a, sa_stream_t stream) {
   const int per_tok = 3 * p.nh * 16;
   const int gy = (per_tok + sp::THREADS - 1) / sp::THREADS;
   int gx = sm_count() * 16 / gy;
-  if (gx > p.B * p.Ll) gx = p.B * p.Ll;
+  if (gx > p.b_count * p.Ll) gx = p.b_count * p.Ll;
   if (gx < 1) gx = 1;
   sp::scatter_qkv_kernel<<<dim3(gx, gy), sp::THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
@@ -169,16 +184,20 @@ extern "C" int sa_sp_scatter_o(const sa_sp_args* a, sa_stream_t stream) {
   if (rc) return rc;
   for (int r = 0; r < a->P; ++r)
     if (!a->dst_a[r]) { set_error("sa_sp_scatter_o: null destination for rank %d", r); return SA_ERR_BAD_ARG; }
-  const int cols = p.hp * 16;
-  if (cols > sp::THREADS) { set_error("sa_sp_scatter_o: more than %d heads per rank", sp::THREADS / 16); return SA_ERR_UNSUPPORTED; }
-  const int rpb = sp::THREADS / cols;
-  const long long n_rows = (long long)p.n_src * p.Ll * p.B;
-  long long gx = (n_rows + rpb - 1) / rpb;
-  if (gx > (long long)sm_count() * 16) gx = (long long)sm_count() * 16;
-  sp::scatter_o_kernel<<<(int)gx, rpb * cols, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, rpb);
+  const long long total = (long long)p.b_count * p.n_src * p.Ll * p.hp * 16;
+  if (total >= (1LL << 31)) { set_error("sa_sp_scatter_o: more than 2^31 chunks in one launch"); return SA_ERR_UNSUPPORTED; }
+  long long gx = (total + 255) / 256;
+  if (gx > (long long)sm_count() * 8) gx = (long long)sm_count() * 8;
+  sp::scatter_o_kernel<<<(int)gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "scatter_o_kernel launch");
   return SA_OK;
+}
+
+extern "C" int sa_sp_set_barrier_timeout_ms(int64_t ms) {
+  if (ms < 0) { sa::set_error("sa_sp_set_barrier_timeout_ms: negative timeout"); return sa::SA_ERR_BAD_ARG; }
+  sa::sp::g_barrier_timeout_ns.store((uint64_t)ms * 1000000ull, std::memory_order_relaxed);
+  return sa::SA_OK;
 }
 
 extern "C" int sa_sp_barrier(void* const* sig, void* epoch, int32_t P, int32_t rank, sa_stream_t stream) {
@@ -190,6 +209,7 @@ extern "C" int sa_sp_barrier(void* const* sig, void* epoch, int32_t P, int32_t r
     if (!p.sig[r]) { set_error("sa_sp_barrier: null flag array for rank %d", r); return SA_ERR_BAD_ARG; }
   p.epoch = reinterpret_cast<uint32_t*>(epoch);
   p.P = P; p.rank = rank;
+  p.timeout_ns = sp::g_barrier_timeout_ns.load(std::memory_order_relaxed);
   sp::barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "barrier_kernel launch");

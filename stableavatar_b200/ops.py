@@ -205,18 +205,46 @@ def gather_rows(src, idx):
 
 def cfg_euler_step(pred, latents, dsigma, audio_scale=0.0, text_scale=0.0, cfg=True, out=None, noise_out=None,
                    dsigma_dev=None):
-    """latents' = bf16(float(latents) + dsigma * CFG(pred)) — sa_cfg_euler_step."""
+    """latents' = bf16(float(latents) + dsigma * CFG(pred)) — sa_cfg_euler_step. latents: bf16, or fp32 for a
+    caller-supplied fp32 sample; the result is bf16 (the model output's dtype)."""
     _need_cuda(pred, latents)
-    assert pred.dtype == latents.dtype == torch.bfloat16 and pred.is_contiguous() and latents.is_contiguous()
+    assert pred.dtype == torch.bfloat16 and latents.dtype in (torch.bfloat16, torch.float32)
+    assert pred.is_contiguous() and latents.is_contiguous()
     n = latents.numel()
     assert pred.numel() == (3 * n if cfg else n)
     if out is None:
-        out = torch.empty_like(latents)
+        out = torch.empty(latents.shape, device=latents.device, dtype=torch.bfloat16)
     L.check(L.lib().sa_cfg_euler_step(C.c_void_p(pred.data_ptr()), C.c_void_p(latents.data_ptr()),
                                       C.c_void_p(out.data_ptr()), C.c_void_p(L.ptr(noise_out)), C.c_int64(n),
                                       C.c_float(audio_scale), C.c_float(text_scale), C.c_float(dsigma), C.c_void_p(L.ptr(dsigma_dev)), int(cfg),
-                                      L.stream_ptr()), "sa_cfg_euler_step")
+                                      L.dt(latents), L.stream_ptr()), "sa_cfg_euler_step")
     return out
+
+
+class WindowBlendArgs(C.Structure):
+    _fields_ = [("new_latents", C.c_void_p), ("pred_latents", C.c_void_p), ("n_windows", C.c_int32), ("C", C.c_int32),
+                ("N", C.c_int32), ("HW", C.c_int32), ("f_max", C.c_int32), ("overlap", C.c_int32), ("pred_dtype", C.c_int32),
+                ("start", C.c_int32 * 64), ("frames", C.c_int32 * 64), ("prev_end", C.c_int32 * 64),
+                ("blend", C.c_int32 * 64), ("weight", C.c_float * 64), ("one_minus_weight", C.c_float * 64)]
+
+
+def window_blend_(pred_latents, new_latents, windows, overlap, weight, one_minus_weight):
+    """Write all windows of a step back into pred_latents [1, C, N, h, w] with the overlap blend, in window order —
+    sa_window_blend. new_latents: bf16 [W, C, f_max, h, w]; windows: (start, frames, prev_end, blend) per window;
+    weight / one_minus_weight: the bf16 tensor values of the reference's weight tensor and of (1 - weight)."""
+    _need_cuda(pred_latents, new_latents)
+    assert new_latents.dtype == torch.bfloat16 and new_latents.is_contiguous() and pred_latents.is_contiguous()
+    assert pred_latents.dim() == 5 and pred_latents.shape[0] == 1 and new_latents.dim() == 5
+    W, Cc, f_max, h, w = new_latents.shape
+    assert len(windows) == W and pred_latents.shape[1] == Cc and tuple(pred_latents.shape[3:]) == (h, w)
+    a = WindowBlendArgs(new_latents=new_latents.data_ptr(), pred_latents=pred_latents.data_ptr(), n_windows=W, C=Cc,
+                        N=pred_latents.shape[2], HW=h * w, f_max=f_max, overlap=overlap, pred_dtype=L.dt(pred_latents))
+    for k, (ws, f, prev_end, blend) in enumerate(windows):
+        a.start[k], a.frames[k], a.prev_end[k], a.blend[k] = ws, f, prev_end, int(blend)
+    for j in range(overlap):
+        a.weight[j], a.one_minus_weight[j] = float(weight[j]), float(one_minus_weight[j])
+    L.check(L.lib().sa_window_blend(C.byref(a), L.stream_ptr()), "sa_window_blend")
+    return pred_latents
 
 
 # ---------------------------------------------------------------------------------------------- Wan VAE ops
@@ -330,30 +358,32 @@ def vae_latent_out(h, wc, bc, mean, std, out):
 class SpArgs(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst_a", C.c_void_p * 8), ("dst_b", C.c_void_p * 8), ("ld", C.c_int64),
                 ("B", C.c_int32), ("Ll", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32), ("P", C.c_int32),
-                ("rank", C.c_int32), ("hg", C.c_int32)]
+                ("rank", C.c_int32), ("hg", C.c_int32), ("b_first", C.c_int32), ("b_count", C.c_int32)]
 
 
-def _sp_args(src, dst_a, dst_b, ld, B, Ll, heads, P, rank, hg):
-    a = SpArgs(src=src.data_ptr(), ld=ld, B=B, Ll=Ll, heads=heads, head_dim=128, P=P, rank=rank, hg=hg)
+def _sp_args(src, dst_a, dst_b, ld, B, Ll, heads, P, rank, hg, b_first=0, b_count=0):
+    a = SpArgs(src=src.data_ptr(), ld=ld, B=B, Ll=Ll, heads=heads, head_dim=128, P=P, rank=rank, hg=hg, b_first=b_first,
+               b_count=b_count)
     for r in range(P):
         a.dst_a[r] = dst_a[r]
         a.dst_b[r] = dst_b[r] if dst_b is not None else None
     return a
 
 
-def sp_scatter_qkv(qkv, kv_ptrs, q_ptrs, *, B, Ll, heads, P, rank, hg):
-    """qkv: local [B*Ll, >= 3*heads*128] bf16 rows (q | k | v) -> peers' kv_recv / q_recv — sa_sp_scatter_qkv."""
+def sp_scatter_qkv(qkv, kv_ptrs, q_ptrs, *, B, Ll, heads, P, rank, hg, b_first=0, b_count=0):
+    """qkv: local [B*Ll, >= 3*heads*128] bf16 rows (q | k | v) -> peers' kv_recv / q_recv — sa_sp_scatter_qkv.
+    b_first / b_count: the CFG samples moved by this launch (0 = all)."""
     _need_cuda(qkv)
     assert qkv.dtype == torch.bfloat16 and qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[0] == B * Ll
-    a = _sp_args(qkv, kv_ptrs, q_ptrs, qkv.stride(0), B, Ll, heads, P, rank, hg)
+    a = _sp_args(qkv, kv_ptrs, q_ptrs, qkv.stride(0), B, Ll, heads, P, rank, hg, b_first, b_count)
     L.check(L.lib().sa_sp_scatter_qkv(C.byref(a), L.stream_ptr()), "sa_sp_scatter_qkv")
 
 
-def sp_scatter_o(o, o_ptrs, *, B, Ll, heads, P, rank, hg):
-    """o: this rank's attention output [P/qs * Ll, B, heads/hg, 128] bf16 contiguous -> peers' o_recv — sa_sp_scatter_o."""
+def sp_scatter_o(o, o_ptrs, *, B, Ll, heads, P, rank, hg, b_first=0, b_count=0):
+    """o: this rank's attention output [B, P/qs * Ll, heads/hg, 128] bf16 contiguous -> peers' o_recv — sa_sp_scatter_o."""
     _need_cuda(o)
     assert o.dtype == torch.bfloat16 and o.is_contiguous()
-    a = _sp_args(o, o_ptrs, None, 0, B, Ll, heads, P, rank, hg)
+    a = _sp_args(o, o_ptrs, None, 0, B, Ll, heads, P, rank, hg, b_first, b_count)
     L.check(L.lib().sa_sp_scatter_o(C.byref(a), L.stream_ptr()), "sa_sp_scatter_o")
 
 
@@ -361,6 +391,13 @@ def sp_barrier(sig_ptrs, epoch, P, rank):
     """Flag barrier across the ranks whose flag arrays are mapped at sig_ptrs — sa_sp_barrier."""
     arr = (C.c_void_p * 8)(*([sig_ptrs[r] for r in range(P)] + [None] * (8 - P)))
     L.check(L.lib().sa_sp_barrier(arr, C.c_void_p(epoch.data_ptr()), P, rank, L.stream_ptr()), "sa_sp_barrier")
+
+
+def sp_set_barrier_timeout_ms(ms: int):
+    """Spin bound of sa_sp_barrier (default 10 min; 0 = unbounded like NCCL) — sa_sp_set_barrier_timeout_ms."""
+    rc = L.lib().sa_sp_set_barrier_timeout_ms(C.c_int64(int(ms)))
+    if rc != 0:
+        raise RuntimeError(f"sa_sp_set_barrier_timeout_ms failed (code {rc}): {L.lib().sa_last_error().decode()}")
 
 
 def ipc_export(t):
@@ -422,14 +459,14 @@ def cross_attn3(q, sets, out=None, accumulate=False, rows_per_group=0, tok_offse
 
 
 def sp_norm_rope_scatter(qkv, weight_q, weight_k, kv_ptrs, q_ptrs, *, B, Ll, heads, P, rank, hg, freqs=None, grid=(1, 1, 1),
-                         tok_offset=0, eps=1e-6):
+                         tok_offset=0, eps=1e-6, b_first=0, b_count=0):
     """RMSNorm + RoPE of the q / k parts of local QKV rows fused with the peer scatter — sa_sp_norm_rope_scatter."""
     _need_cuda(qkv)
     assert qkv.dtype == torch.bfloat16 and qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[0] == B * Ll
     assert weight_q.dtype == weight_k.dtype == torch.bfloat16
     if freqs is not None:
         assert freqs.dtype == torch.float32 and freqs.shape == (1024, 64, 2) and freqs.is_contiguous()
-    a = _sp_args(qkv, kv_ptrs, q_ptrs, qkv.stride(0), B, Ll, heads, P, rank, hg)
+    a = _sp_args(qkv, kv_ptrs, q_ptrs, qkv.stride(0), B, Ll, heads, P, rank, hg, b_first, b_count)
     L.check(L.lib().sa_sp_norm_rope_scatter(C.byref(a), C.c_void_p(weight_q.data_ptr()), C.c_void_p(weight_k.data_ptr()),
                                             C.c_void_p(L.ptr(freqs)), grid[0], grid[1], grid[2], tok_offset, C.c_float(eps),
                                             L.stream_ptr()), "sa_sp_norm_rope_scatter")

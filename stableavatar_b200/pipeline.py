@@ -1,27 +1,42 @@
 """Inference pipeline: the scheduler loop with 3-way text+audio CFG and the sliding window over latent frames.
 
 Mirrors `WanI2VTalkingInferenceLongPipeline` of wan/pipeline/wan_inference_long_pipeline.py (ctor :193-216, `__call__`
-:540-806): same constructor arguments, same `__call__` keyword arguments, `.videos` on the result. The context
-producers (T5, CLIP, Wav2Vec2, VAE encode) are the caller's modules and are only invoked, never re-implemented
-(out of scope); the loop body — DiT forward, CFG combine, Euler step, overlap blend, VAE decode — runs on
-the B200 kernels. `denoise()` is the hot path proper and takes already-encoded conditioning, so it can be driven with
-synthetic features (bench.py).
+:540-806, `check_inputs` :468-507, output class :173-185) and the part of `DiffusionPipeline` the reference entry point
+touches (`.to(device=...)`, inference.py:524): same constructor arguments, same `__call__` keyword arguments and
+`ValueError`s, `.videos` on the result. The context producers (T5, CLIP, Wav2Vec2) are the caller's modules and are only
+invoked, never re-implemented (out of scope); the loop body — DiT forward, CFG combine, Euler step,
+overlap blend, VAE encode / decode — runs on the B200 kernels. `denoise()` is the hot path proper and takes
+already-encoded conditioning, so it can be driven with synthetic features (bench.py).
 
-Differences from the reference loop that do not change results: wav2vec features are computed once per window
-instead of once per window per step (pipe.py:727-729 recomputes identical values), and `torch.cuda.empty_cache()`
-(pipe.py:755) is not called. One deliberate difference in control flow: when the clip has exactly one window
-(`infer_length == frames_per_batch`) the reference's `while` (pipe.py:714, 781-789) never terminates; here that window
-is processed once.
+Restructurings of the reference loop that do not change results:
+  * wav2vec features are computed once per window instead of once per window per step (pipe.py:727-729 recomputes
+    identical values), and `torch.cuda.empty_cache()` (pipe.py:755) is not called;
+  * the text / CLIP MLPs and the per-block text / image K, V projections depend only on the prompt and the reference
+    image: they are computed once per clip (`WanTransformer3DFantasyModel.encode_context`) instead of in every forward;
+  * the windows of one step read the same `latents_all` and share weights and timestep, so windows of equal shape run
+    as ONE forward (`cfg_groups`), and the write-back with the overlap blend of all windows is one kernel
+    (`sa_window_blend`) that walks the windows in the reference's order;
+  * each window shape is captured once as a CUDA graph and replayed (conditioning lives in static buffers).
+One deliberate difference in control flow: when the clip has exactly one window (`infer_length == frames_per_batch`) the
+reference's `while` (pipe.py:714, 781-789) never terminates; here that window is processed once. The memory modes
+(`enable_model_cpu_offload`, `enable_sequential_cpu_offload`, fp8 weights) are out of scope on a 180 GB part and raise.
 """
 from __future__ import annotations
 
 import math
-from types import SimpleNamespace
+from collections import OrderedDict
+from dataclasses import dataclass
 
 import numpy as np
 import torch
 
 from . import ops
+
+
+@dataclass
+class WanI2VPipelineTalkingInferenceLongOutput:
+    """pipe.py:173-185."""
+    videos: torch.Tensor
 
 
 def window_schedule(infer_length, frames_per_batch, overlap):
@@ -44,7 +59,7 @@ def window_schedule(infer_length, frames_per_batch, overlap):
 
 
 def overlap_weights(n, scheme, device, dtype):
-    """pipe.py:756-766."""
+    """pipe.py:756-766: the weight tensor in `dtype` (assigning into the zeros tensor rounds each value to it)."""
     if scheme == "uniform":
         w = torch.tensor([j / (n - 1) for j in range(n)], dtype=torch.float32)
     elif scheme == "log":
@@ -72,32 +87,57 @@ def _frames_kwarg(transformer, clip_length):
     return {}
 
 
+def _dsigma_at(scheduler, i):
+    """sigma_{i+1} - sigma_i as the fp32 tensor subtraction of FlowMatchEulerDiscreteScheduler.step. The repo scheduler
+    answers from its host table; any scheduler with a `.sigmas` table (diffusers') works too."""
+    if hasattr(scheduler, "dsigma_at"):
+        return scheduler.dsigma_at(i)
+    sig = scheduler.sigmas
+    return float((sig[i + 1].float() - sig[i].float()).item())
+
+
+def _cond_key(prompt_embeds, clip_context, y):
+    """Identity + version of the conditioning tensors: changes when the caller passes other tensors or overwrites them."""
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (y, clip_context, *prompt_embeds))
+
+
 class GraphedDenoiseStep:
-    """One window of one step — DiT forward on the CFG batch + CFG combine + Euler update — captured once as CUDA
-    graph(s) and replayed for every step of that window shape: the ~650 kernel launches of a step (≈ 80 ms of host
-    time) then cost nothing, which matters most under sequence parallelism where a step is only ~100 ms of GPU work.
-    Under sequence parallelism the NCCL all-to-alls stay eager and split the capture into segments
-    (sequence_parallel.SegmentedGraph). Step-dependent scalars (timestep, sigma difference) live in device buffers."""
+    """W windows of one step — DiT forward on the W CFG triples + CFG combine + Euler update — captured once as CUDA
+    graph(s) and replayed for every step of that shape: the ~600 kernel launches of a step (≈ 80 ms of host time) then
+    cost nothing, which matters most under sequence parallelism where a step is only ~100 ms of GPU work. Everything the
+    graph reads lives in buffers it owns — latents, timestep, sigma difference, audio features, `y`, and the
+    ContextCache of the prompt / CLIP conditioning — so a new clip only re-fills them (`denoise_step`) and the cache
+    key holds shapes and scalars only. Under sequence parallelism with the NCCL fallback the all-to-alls stay eager and
+    split the capture into segments (sequence_parallel.SegmentedGraph)."""
 
     def __init__(self, pipe, latents, prompt_embeds, clip_context, y, vocal_embeddings, *, seq_len, clip_length,
-                 text_guide_scale, audio_guide_scale, do_cfg):
+                 text_guide_scale, audio_guide_scale, do_cfg, pool=None):
         dev = latents.device
+        W, f = latents.shape[0], latents.shape[2]
         n = 3 if do_cfg else 1
+        tr = pipe.transformer
+        self.W, self.n = W, n
         self.lat = latents.clone()
-        self.t = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.t = torch.zeros(n * W, device=dev, dtype=torch.float32)
         self.ds = torch.zeros(1, device=dev, dtype=torch.float32)
         self.vocal = vocal_embeddings.clone()
+        self.y = y[:, :, :f].repeat(W, 1, 1, 1, 1).contiguous()
+        self.out = torch.empty(latents.shape, device=dev, dtype=torch.bfloat16)
+        self.ctx = tr.encode_context(list(prompt_embeds) * W, clip_context.repeat(W, 1, 1))
+        self.cond_key = _cond_key(prompt_embeds, clip_context, y)     # what y / ctx currently hold (denoise_step refills them)
 
         def run():
-            x = self.lat.expand(n, -1, -1, -1, -1).contiguous() if n > 1 else self.lat
-            pred = pipe.transformer(x=x, context=prompt_embeds, t=self.t, seq_len=seq_len, y=y[:, :, :self.lat.size(2)],
-                                    clip_fea=clip_context, vocal_embeddings=self.vocal, is_clip_level_modeling=False,
-                                    **_frames_kwarg(pipe.transformer, clip_length))
-            return ops.cfg_euler_step(pred.contiguous(), self.lat, 0.0, audio_scale=float(audio_guide_scale or 0.0),
-                                      text_scale=float(text_guide_scale or 0.0), cfg=do_cfg, dsigma_dev=self.ds)
+            x = self.lat.repeat_interleave(n, dim=0) if n > 1 else self.lat
+            pred = tr(x=x, context=self.ctx, t=self.t, seq_len=seq_len, y=self.y, clip_fea=None,
+                      vocal_embeddings=self.vocal, is_clip_level_modeling=False, cfg_groups=W,
+                      **_frames_kwarg(tr, clip_length)).contiguous()
+            for k in range(W):
+                ops.cfg_euler_step(pred[n * k:n * (k + 1)], self.lat[k:k + 1], 0.0, audio_scale=float(audio_guide_scale or 0.0),
+                                   text_scale=float(text_guide_scale or 0.0), cfg=do_cfg, dsigma_dev=self.ds, out=self.out[k:k + 1])
+            return self.out
 
         from .sequence_parallel import SegmentedGraph
-        self.graph = SegmentedGraph(run, device=dev)
+        self.graph = SegmentedGraph(run, device=dev, pool=pool)
 
     def __call__(self, latents, t, dsigma, vocal_embeddings=None):
         self.lat.copy_(latents)
@@ -112,84 +152,224 @@ class GraphedDenoiseStep:
 
 
 class WanI2VTalkingInferenceLongPipeline:
+    _callback_tensor_inputs = ["latents", "prompt_embeds", "negative_prompt_embeds"]       # pipe.py:199-203
+    max_graphs = 6                     # captured window shapes kept (least recently used evicted)
+
     def __init__(self, tokenizer=None, text_encoder=None, vae=None, transformer=None, clip_image_encoder=None,
                  scheduler=None, wav2vec_processor=None, wav2vec=None):
         self.tokenizer, self.text_encoder, self.vae, self.transformer = tokenizer, text_encoder, vae, transformer
         self.clip_image_encoder, self.scheduler = clip_image_encoder, scheduler
         self.wav2vec_processor, self.wav2vec = wav2vec_processor, wav2vec
         self.use_cuda_graphs = True      # replay a captured graph per window shape (off automatically with TeaCache)
-        self._graphs = {}
+        self.max_windows_per_forward = 4  # windows of one step batched into one forward
+        self._graphs = OrderedDict()
+        self._graph_pool = None
+        self._ctx_memo = None
+
+    # ------------------------------------------------------------------ DiffusionPipeline surface used by inference.py / app.py
+    @property
+    def _execution_device(self):
+        return self.transformer.device
+
+    def to(self, *args, **kwargs):
+        """`pipeline.to(device=device)` (inference.py:524): every torch module of the pipeline moves; a dtype, if given,
+        applies to floating-point modules as in DiffusionPipeline.to. The wav2vec model stays where the caller put it
+        (the reference keeps it on the CPU, inference.py:489) unless it is already on an accelerator."""
+        device = kwargs.get("device", None)
+        dtype = kwargs.get("dtype", kwargs.get("torch_dtype", None))
+        for a in args:
+            if isinstance(a, torch.dtype):
+                dtype = a
+            elif a is not None:
+                device = a
+        for name in ("text_encoder", "vae", "transformer", "clip_image_encoder"):
+            m = getattr(self, name)
+            if m is None or not hasattr(m, "to"):
+                continue
+            if device is not None:
+                m = m.to(device)
+            if dtype is not None and name != "vae":            # the VAE boundary is fp32 (pipe.py:424-430)
+                m = m.to(dtype)
+            setattr(self, name, m)
+        self._graphs.clear()
+        self._ctx_memo = None
+        return self
+
+    def _no_offload(self, *a, **k):
+        raise NotImplementedError("CPU-offload memory modes are out of scope on the B200 path (180 GB HBM): use "
+                                  "pipeline.to(device=...) — GPU_memory_mode='model_full_load' in inference.py")
+    enable_model_cpu_offload = enable_sequential_cpu_offload = _no_offload
+
+    def maybe_free_model_hooks(self):
+        pass
+
+    def check_inputs(self, prompt, height, width, negative_prompt, callback_on_step_end_tensor_inputs,
+                     prompt_embeds=None, negative_prompt_embeds=None):
+        """pipe.py:458-507, same conditions and messages. The B200 DiT additionally needs whole 2x2 patches."""
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if callback_on_step_end_tensor_inputs is not None and not all(
+                k in self._callback_tensor_inputs for k in callback_on_step_end_tensor_inputs):
+            raise ValueError(
+                f"`callback_on_step_end_tensor_inputs` has to be in {self._callback_tensor_inputs}, but found "
+                f"{[k for k in callback_on_step_end_tensor_inputs if k not in self._callback_tensor_inputs]}")
+        if prompt is not None and prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `prompt`: {prompt} and `prompt_embeds`: {prompt_embeds}. Please make sure to"
+                             " only forward one of the two.")
+        elif prompt is None and prompt_embeds is None:
+            raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both `prompt` and `prompt_embeds` undefined.")
+        elif prompt is not None and (not isinstance(prompt, str) and not isinstance(prompt, list)):
+            raise ValueError(f"`prompt` has to be of type `str` or `list` but is {type(prompt)}")
+        if prompt is not None and negative_prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `prompt`: {prompt} and `negative_prompt_embeds`:"
+                             f" {negative_prompt_embeds}. Please make sure to only forward one of the two.")
+        if negative_prompt is not None and negative_prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `negative_prompt`: {negative_prompt} and `negative_prompt_embeds`:"
+                             f" {negative_prompt_embeds}. Please make sure to only forward one of the two.")
+        if prompt_embeds is not None and negative_prompt_embeds is not None and torch.is_tensor(prompt_embeds) \
+                and torch.is_tensor(negative_prompt_embeds) and prompt_embeds.shape != negative_prompt_embeds.shape:
+            raise ValueError("`prompt_embeds` and `negative_prompt_embeds` must have the same shape when passed directly, but"
+                             f" got: `prompt_embeds` {prompt_embeds.shape} != `negative_prompt_embeds`"
+                             f" {negative_prompt_embeds.shape}.")
+        if height % 16 != 0 or width % 16 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 16 (8x VAE, 2x2 patches) but are {height} and {width}.")
 
     # ------------------------------------------------------------------ hot path
+    def _graph_for(self, key, build):
+        g = self._graphs.get(key)
+        if g is None:
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.popitem(last=False)
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            g = self._graphs[key] = build(self._graph_pool)
+        else:
+            self._graphs.move_to_end(key)
+        return g
+
     @torch.no_grad()
     def denoise_step(self, latents, t, dsigma, prompt_embeds, clip_context, y, vocal_embeddings, *, seq_len,
                      clip_length, text_guide_scale, audio_guide_scale, do_cfg=True):
-        """One window of one step (pipe.py:730-754): DiT forward on the CFG batch, CFG combine, Euler update.
-        latents [1,16,f,h,w] bf16 -> new latents (bf16)."""
-        tc = getattr(self.transformer, "teacache", None)
-        fp32 = getattr(self.transformer, "dtype", None) == torch.float32      # fp32 parity mode: eager, fp32 CFG + Euler
-        if self.use_cuda_graphs and tc is None and not fp32 and getattr(self.transformer, "hooks", None) is None:
-            key = (tuple(latents.shape), tuple(vocal_embeddings.shape), seq_len, clip_length, float(text_guide_scale or 0),
-                   float(audio_guide_scale or 0), do_cfg, y.data_ptr(), clip_context.data_ptr(),
-                   tuple(p.data_ptr() for p in prompt_embeds))
-            g = self._graphs.get(key)
-            if g is None:
-                g = self._graphs[key] = GraphedDenoiseStep(
-                    self, latents, prompt_embeds, clip_context, y, vocal_embeddings, seq_len=seq_len, clip_length=clip_length,
-                    text_guide_scale=text_guide_scale, audio_guide_scale=audio_guide_scale, do_cfg=do_cfg)
-            return g(latents, t, dsigma, vocal_embeddings).clone()
+        """W windows of one step (pipe.py:730-754, W = latents.shape[0], usually 1): DiT forward on the CFG batch, CFG
+        combine, Euler update. latents [W,16,f,h,w] (bf16, or the caller's fp32) -> new latents [W,16,f,h,w].
+        prompt_embeds / clip_context / y are the conditioning of ONE CFG triple; vocal_embeddings [3W, T, 768]."""
+        tr = self.transformer
+        W = latents.shape[0]
         n = 3 if do_cfg else 1
-        x = latents.expand(n, -1, -1, -1, -1).contiguous() if n > 1 else latents
-        tt = t.expand(n) if torch.is_tensor(t) else torch.full((n,), float(t), device=latents.device)
-        noise_pred = self.transformer(x=x, context=prompt_embeds, t=tt, seq_len=seq_len, y=y[:, :, :latents.size(2)],
-                                      clip_fea=clip_context, vocal_embeddings=vocal_embeddings,
-                                      is_clip_level_modeling=False, **_frames_kwarg(self.transformer, clip_length))
+        tc = getattr(tr, "teacache", None)
+        fp32 = getattr(tr, "dtype", None) == torch.float32      # fp32 parity mode: eager, fp32 CFG + Euler
+        plain = tc is not None or fp32 or getattr(tr, "hooks", None) is not None or not hasattr(tr, "encode_context")
+        if plain and W != 1:
+            raise ValueError("window batching is not available with TeaCache / fp32 mode / hooks (one window per forward)")
+        latents = latents.contiguous()
+        if self.use_cuda_graphs and not plain:
+            key = (tuple(latents.shape), latents.dtype, tuple(vocal_embeddings.shape), tuple(y.shape), seq_len, clip_length,
+                   float(text_guide_scale or 0), float(audio_guide_scale or 0), do_cfg,
+                   tuple(tuple(p.shape) for p in prompt_embeds))
+            g = self._graph_for(key, lambda pool: GraphedDenoiseStep(
+                self, latents, prompt_embeds, clip_context, y, vocal_embeddings, seq_len=seq_len, clip_length=clip_length,
+                text_guide_scale=text_guide_scale, audio_guide_scale=audio_guide_scale, do_cfg=do_cfg, pool=pool))
+            ck = _cond_key(prompt_embeds, clip_context, y)
+            if ck != g.cond_key:                                  # new clip (or overwritten tensors): refill, re-encode once
+                g.y.copy_(y[:, :, :g.y.shape[2]].repeat(W, 1, 1, 1, 1))
+                tr.encode_context(list(prompt_embeds) * W, clip_context.repeat(W, 1, 1), out=g.ctx)
+                g.cond_key = ck
+            return g(latents, t, dsigma, vocal_embeddings).clone()
+        x = latents.repeat_interleave(n, dim=0) if n > 1 else latents
+        tt = t.expand(n * W) if torch.is_tensor(t) else torch.full((n * W,), float(t), device=latents.device)
+        f = latents.size(2)
+        if plain:
+            ctx, clip, kw = prompt_embeds, clip_context, {}
+        else:                                                     # eager bf16 path: context encoded once per conditioning
+            ck = (_cond_key(prompt_embeds, clip_context, y), W)
+            if self._ctx_memo is None or self._ctx_memo[0] != ck:
+                self._ctx_memo = (ck, tr.encode_context(list(prompt_embeds) * W, clip_context.repeat(W, 1, 1)))
+            ctx, clip, kw = self._ctx_memo[1], None, dict(cfg_groups=W)
+        noise_pred = tr(x=x, context=ctx, t=tt, seq_len=seq_len, y=y[:, :, :f].repeat(W, 1, 1, 1, 1) if W > 1 else y[:, :, :f],
+                        clip_fea=clip, vocal_embeddings=vocal_embeddings, is_clip_level_modeling=False,
+                        **_frames_kwarg(tr, clip_length), **kw).contiguous()
         if fp32:
             from . import fp32_mode
-            step = fp32_mode.cfg_euler_step
-        else:
-            step = ops.cfg_euler_step
-        return step(noise_pred.contiguous(), latents.contiguous(), dsigma, audio_scale=float(audio_guide_scale or 0.0),
-                    text_scale=float(text_guide_scale or 0.0), cfg=do_cfg)
+            return fp32_mode.cfg_euler_step(noise_pred, latents, dsigma, audio_scale=float(audio_guide_scale or 0.0),
+                                            text_scale=float(text_guide_scale or 0.0), cfg=do_cfg)
+        out = torch.empty(latents.shape, device=latents.device, dtype=torch.bfloat16)
+        for k in range(W):
+            ops.cfg_euler_step(noise_pred[n * k:n * (k + 1)], latents[k:k + 1], dsigma, audio_scale=float(audio_guide_scale or 0.0),
+                               text_scale=float(text_guide_scale or 0.0), cfg=do_cfg, out=out[k:k + 1])
+        return out
 
     @torch.no_grad()
     def denoise(self, latents_all, prompt_embeds, clip_context, y, vocal_embeddings_fn, *, num_inference_steps,
                 clip_length=81, text_guide_scale=3.0, audio_guide_scale=5.0, overlap_window_length=5,
                 overlapping_weight_scheme="uniform", do_cfg=True, seq_len=None, callback=None):
         """The 50-step loop over all windows (pipe.py:704-791). vocal_embeddings_fn(index_start, index_end,
-        is_last_window) -> wav2vec features [1,T,768] of that window. Returns the final latents_all."""
+        is_last_window) -> wav2vec features [1,T,768] of that window. Returns the final latents_all (caller's dtype)."""
         dev = latents_all.device
         fpb = (clip_length - 1) // 4 + 1
         self.scheduler.set_timesteps(num_inference_steps, device=dev, mu=1)
         timesteps = self.scheduler.timesteps
-        infer_length = latents_all.size(2)
+        n_lat = infer_length = latents_all.size(2)
         h, w = latents_all.shape[-2:]
         if seq_len is None:
             ps = self.transformer.config.patch_size
             seq_len = math.ceil((h * w) / (ps[1] * ps[2]) * fpb)
         windows = window_schedule(infer_length, fpb, overlap_window_length)
-        n_lat = latents_all.shape[2]
-        audio_cache = {}
+        tr = self.transformer
+        batching = (getattr(tr, "teacache", None) is None and getattr(tr, "dtype", None) != torch.float32
+                    and getattr(tr, "hooks", None) is None and hasattr(tr, "encode_context") and do_cfg)
+        n = 3 if do_cfg else 1
+        audio = []
+        for (ws, we, _) in windows:
+            v = vocal_embeddings_fn(ws, we, we == infer_length).to(dev, getattr(tr, "dtype", torch.bfloat16))
+            # pipe.py:736-737: the [0, v, v] batch is built whenever both scales are given
+            audio.append(torch.cat([torch.zeros_like(v), v, v]) if (text_guide_scale is not None and audio_guide_scale is not None) else v)
+        # windows of equal (frames, audio length) run as one forward, at most max_windows_per_forward at a time
+        groups, by_shape = [], {}
+        for k, (ws, we, _) in enumerate(windows):
+            key = (we - ws, audio[k].shape[1]) if batching else k
+            g = by_shape.get(key)
+            if g is None or len(g) >= max(1, self.max_windows_per_forward if batching else 1):
+                g = by_shape[key] = []
+                groups.append(g)
+            g.append(k)
+        group_audio = [torch.cat([audio[k] for k in g]) for g in groups]
+        fused_blend = latents_all.dtype in (torch.bfloat16, torch.float32) and getattr(tr, "dtype", None) != torch.float32 \
+            and overlap_window_length <= 64 and len(windows) <= 64
+        if fused_blend and overlap_window_length > 0:
+            ow = overlap_weights(overlap_window_length, overlapping_weight_scheme, "cpu", torch.bfloat16).flatten()
+            w_host, omw_host = ow.float().tolist(), (1 - ow).float().tolist()
+        else:
+            w_host, omw_host = [], []
         for i, t in enumerate(timesteps):
             pred_latents = torch.zeros_like(latents_all)
-            for (ws, we, prev_end) in windows:
-                self.scheduler._step_index = None
-                idx = [ii % n_lat for ii in range(ws, we)]
-                latents = latents_all[:, :, idx].clone()
-                if (ws, we) not in audio_cache:
-                    v = vocal_embeddings_fn(ws, we, we == infer_length).to(dev, latents_all.dtype)
-                    audio_cache[(ws, we)] = torch.cat([torch.zeros_like(v), v, v]) if do_cfg else v
-                latents = self.denoise_step(latents, t, self.scheduler.dsigma_at(i), prompt_embeds, clip_context, y,
-                                            audio_cache[(ws, we)], seq_len=seq_len, clip_length=clip_length,
-                                            text_guide_scale=text_guide_scale, audio_guide_scale=audio_guide_scale,
-                                            do_cfg=do_cfg)
-                if ws != 0 and i != 0:                                       # overlap blend, pipe.py:756-771
-                    ow = overlap_weights(overlap_window_length, overlapping_weight_scheme, dev, latents.dtype)
-                    s_idx = [ii % latents.shape[2] for ii in range(overlap_window_length)]
-                    e_idx = [ii % n_lat for ii in range(prev_end - overlap_window_length, prev_end)]
-                    latents[:, :, s_idx] = latents[:, :, s_idx] * ow + pred_latents[:, :, e_idx] * (1 - ow)
-                latents = latents.to(torch.bfloat16).to(pred_latents.dtype)   # the bf16 write-back is hard-wired, pipe.py:774/779
-                pred_latents[:, :, [(ws + k) % n_lat for k in range(latents.size(2))]] = latents
+            ds = _dsigma_at(self.scheduler, i)
+            new_all = torch.empty(len(windows), latents_all.shape[1], fpb, h, w, device=dev, dtype=torch.bfloat16) if fused_blend else None
+            results = {}
+            for g, ga in zip(groups, group_audio):
+                if hasattr(self.scheduler, "_step_index"):
+                    self.scheduler._step_index = None
+                lat = torch.cat([latents_all[:, :, [ii % n_lat for ii in range(windows[k][0], windows[k][1])]] for k in g])
+                out = self.denoise_step(lat, t, ds, prompt_embeds, clip_context, y, ga, seq_len=seq_len,
+                                        clip_length=clip_length, text_guide_scale=text_guide_scale,
+                                        audio_guide_scale=audio_guide_scale, do_cfg=do_cfg)
+                for j, k in enumerate(g):
+                    if fused_blend:
+                        new_all[k, :, :out.shape[2]] = out[j]
+                    else:
+                        results[k] = out[j:j + 1]
+            if fused_blend:                                                   # pipe.py:756-779 for every window, one launch
+                meta = [(ws, we - ws, prev_end, ws != 0 and i != 0) for (ws, we, prev_end) in windows]
+                ops.window_blend_(pred_latents, new_all, meta, overlap_window_length if i != 0 else 0, w_host, omw_host)
+            else:
+                for k, (ws, we, prev_end) in enumerate(windows):
+                    latents = results[k]
+                    if ws != 0 and i != 0:
+                        ow = overlap_weights(overlap_window_length, overlapping_weight_scheme, dev, latents.dtype)
+                        s_idx = [ii % latents.shape[2] for ii in range(overlap_window_length)]
+                        e_idx = [ii % n_lat for ii in range(prev_end - overlap_window_length, prev_end)]
+                        latents[:, :, s_idx] = latents[:, :, s_idx] * ow + pred_latents[:, :, e_idx] * (1 - ow)
+                    latents = latents.to(torch.bfloat16).to(pred_latents.dtype)   # the bf16 write-back is hard-wired, pipe.py:774/779
+                    pred_latents[:, :, [(ws + kk) % n_lat for kk in range(latents.size(2))]] = latents
             latents_all = pred_latents
             if callback is not None:
                 callback(i, t, latents_all)
@@ -215,11 +395,15 @@ class WanI2VTalkingInferenceLongPipeline:
         """Same keyword arguments as pipe.py:540-578. Conditioning may be passed pre-encoded (`prompt_embeds` /
         `negative_prompt_embeds` lists of [L,4096], `clip_context` [1,257,1280], `cond_image` [1,3,1,H,W] in [-1,1],
         `vocal_embeddings_fn`) — otherwise the injected encoders are called exactly where the reference calls them."""
-        if height % 16 != 0 or width % 16 != 0:
-            raise ValueError(f"`height` and `width` have to be divisible by 16 but are {height} and {width}.")   # pipe.py:478
-        dev = self.transformer.device
+        self.check_inputs(prompt, height, width, negative_prompt, callback_on_step_end_tensor_inputs, prompt_embeds,
+                          negative_prompt_embeds)
+        dev = self._execution_device
         bf = torch.bfloat16
+        weight_dtype = getattr(self.text_encoder, "dtype", bf) if self.text_encoder is not None else bf
         do_cfg = guidance_scale > 1.0
+        if do_cfg and (text_guide_scale is None or audio_guide_scale is None):
+            raise ValueError("classifier-free guidance (guidance_scale > 1) needs both `text_guide_scale` and "
+                             "`audio_guide_scale` (pipe.py:736-753 combines the three predictions with them)")
         if prompt_embeds is None:
             prompt_embeds, negative_prompt_embeds = self.encode_prompt(prompt, negative_prompt, do_cfg,
                                                                        max_sequence_length=max_sequence_length, device=dev)
@@ -232,10 +416,14 @@ class WanI2VTalkingInferenceLongPipeline:
         max_audio_index = vocal_input_values.shape[0]
         total_frames = int(max_audio_index / audio_token_per_frame)
         shape = (1, 16, (total_frames - 1) // tcr + 1, height // scr, width // scr)
-        if latents is None:
+        if latents is None:                                                     # prepare_latents, pipe.py:363-386
             latents = torch.randn(shape, generator=generator, device=generator.device if generator is not None else dev,
-                                  dtype=bf).to(dev)
-        latents_all = latents.to(dev, bf).clone()
+                                  dtype=weight_dtype).to(dev)
+        else:
+            latents = latents.to(dev)                                           # the caller's dtype is kept
+        if hasattr(self.scheduler, "init_noise_sigma"):
+            latents = latents * self.scheduler.init_noise_sigma
+        latents_all = latents.clone()
         infer_length = latents_all.size(2)
 
         if cond_image is None:
@@ -245,7 +433,7 @@ class WanI2VTalkingInferenceLongPipeline:
             arr = (arr - 0.5) * 2
             cond_image = arr.unsqueeze(1).unsqueeze(0)
             if clip_context is None:
-                clip_context = self.clip_image_encoder([arr.to(dev, bf)[:, None, :, :]])
+                clip_context = self.clip_image_encoder([arr.to(dev, weight_dtype)[:, None, :, :]])
         cond_image = cond_image.to(dev)
         clip_context = clip_context.to(dev, bf)
         if do_cfg:
@@ -284,7 +472,7 @@ class WanI2VTalkingInferenceLongPipeline:
             video = self.decode_latents(lat)
         if not return_dict:
             video = torch.from_numpy(video) if isinstance(video, np.ndarray) else video
-        return SimpleNamespace(videos=video)
+        return WanI2VPipelineTalkingInferenceLongOutput(videos=video)
 
     def encode_prompt(self, prompt, negative_prompt, do_cfg, max_sequence_length=512, device=None):
         """pipe.py:258-361 — T5 through the injected tokenizer/text_encoder (caller-side modules)."""

@@ -42,9 +42,9 @@ class SegmentedGraph:
     With no communication (single GPU) this degenerates to one ordinary CUDA graph."""
     _active = None
 
-    def __init__(self, fn, device=None):
+    def __init__(self, fn, device=None, pool=None):
         self.segments, self.cur = [], None
-        self.pool = torch.cuda.graph_pool_handle()
+        self.pool = pool if pool is not None else torch.cuda.graph_pool_handle()   # shareable between window shapes
         self.stream = torch.cuda.Stream(device=device)
         self.stream.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(self.stream):
@@ -167,22 +167,33 @@ def exchange_out(pl, O, B, Ll, nh, d, group=None):
 class PeerExchange:
     """The self-attention all-to-alls as direct peer stores (csrc/sp_exchange.cu) instead of NCCL: every rank maps the
     receive buffers and flag arrays of all ranks of the group through CUDA IPC (sa_ipc_export / sa_ipc_open, handles
-    exchanged once with all_gather_object); per block the rank then runs
-        scatter_qkv -> barrier -> attention on its receive buffers -> scatter_o -> barrier -> o_recv is [B, Ll, nh, d].
-    Single buffers suffice: a peer overwrites kv/q_recv only after the second barrier of the block, which this rank
-    passes after its attention has read them, and o_recv only after the first barrier of the next block, which comes
-    after the output projection. Everything is an ordinary kernel on the current stream, so the whole step is captured
-    in one CUDA graph (no comm_point splits)."""
+    exchanged once with all_gather_object). Buffers are batch-outermost — kv_recv [B, P, Ll, 2, hp, d], q_recv
+    [B, n_src, Ll, hp, d], attention output o_send [B, n_src * Ll, hp, d], o_recv [B, Ll, nh, d] — so one CFG sample is a
+    contiguous slice and the exchange is pipelined per sample (`attention`):
+
+        comm stream :  norm+RoPE+scatter(b0) | barrier | norm+RoPE+scatter(b1) | barrier | ...
+        stream b    :                          wait    | attention(b) | scatter_o(b)
+        main stream :  join of all sample streams | barrier | (output projection reads o_recv)
+
+    so only the first sample's scatter, the last sample's O scatter and two barriers are exposed; the rest of the NVLink
+    traffic runs under the attention of the neighbouring samples. Two independent flag sets keep the comm-stream barriers
+    and the main-stream barrier apart. Single buffers suffice: a peer overwrites kv/q_recv only in the next block, after
+    the main-stream barrier which every rank reaches after its attention kernels; o_recv only after the next block's comm
+    barrier, which this rank reaches after its output projection. Everything is ordinary kernels + events, so the whole
+    step is captured in one CUDA graph (the side streams fork from and rejoin the capturing stream)."""
 
     def __init__(self, pl, B, Ll, nh, d, device, group=None):
-        self.pl, self.shape, self.group = pl, (B, Ll, nh, d), group
-        P, hp = pl.world, pl.hp
+        self.pl, self.shape, self.group, self.device = pl, (B, Ll, nh, d), group, device
+        P, hp, n_src = pl.world, pl.hp, len(pl.q_sources)
         bf = torch.bfloat16
-        self.kv_recv = torch.empty(P * Ll * B * 2 * hp * d, device=device, dtype=bf)
-        self.q_recv = torch.empty(len(pl.q_sources) * Ll * B * hp * d, device=device, dtype=bf)
-        self.o_recv = torch.empty(B * Ll * nh * d, device=device, dtype=bf)
-        self.sig = torch.zeros(64, device=device, dtype=torch.int32)
-        self.epoch = torch.zeros(1, device=device, dtype=torch.int32)
+        self.kv_recv = torch.empty(B, P * Ll, 2, hp, d, device=device, dtype=bf)
+        self.q_recv = torch.empty(B, n_src * Ll, hp, d, device=device, dtype=bf)
+        self.o_send = torch.empty(B, n_src * Ll, hp, d, device=device, dtype=bf)
+        self.o_recv = torch.empty(B, Ll, nh, d, device=device, dtype=bf)
+        self.sig = torch.zeros(2, 64, device=device, dtype=torch.int32)          # [main | comm] flag sets
+        self.epoch = torch.zeros(2, device=device, dtype=torch.int32)
+        self.comm = torch.cuda.Stream(device=device)
+        self.sample_streams = [torch.cuda.Stream(device=device) for _ in range(B)]
         torch.cuda.synchronize(device)
         local = (self.kv_recv, self.q_recv, self.o_recv, self.sig)
         metas = [None] * P
@@ -198,7 +209,8 @@ class PeerExchange:
                     if (r, handle) not in self._bases:       # buffers of one peer may share a cudaMalloc segment
                         self._bases[(r, handle)] = ops.ipc_open(handle)
                     ptrs[j].append(self._bases[(r, handle)] + off)
-        self.kv_ptrs, self.q_ptrs, self.o_ptrs, self.sig_ptrs = ptrs
+        self.kv_ptrs, self.q_ptrs, self.o_ptrs, sig0 = ptrs
+        self.sig_ptrs = [sig0, [q + 64 * 4 for q in sig0]]
         dist.barrier(group=group)                               # every rank has mapped every buffer before the first store
 
     def close(self):
@@ -218,48 +230,105 @@ class PeerExchange:
         except Exception:  # noqa: BLE001
             pass
 
-    def barrier(self):
-        ops.sp_barrier(self.sig_ptrs, self.epoch, self.pl.world, self.pl.rank)
+    def barrier(self, which=0):
+        ops.sp_barrier(self.sig_ptrs[which], self.epoch[which:which + 1], self.pl.world, self.pl.rank)
 
-    def exchange_qkv(self, qkv):
-        """qkv: local [B*Ll, 3*nh*d] rows after RMSNorm+RoPE. Returns (Q [Lq, B, hp, d], KV [L, B, 2, hp, d])."""
+    def scatter_qkv(self, qkv, norm, b_first=0, b_count=0):
+        """Local [B*Ll, 3*nh*d] projection rows -> the peers' q_recv / kv_recv. norm = (weight_q, weight_k, freqs, grid,
+        tok_offset): RMSNorm + RoPE of q / k fused into the scatter (the normalised values only ever exist in the receive
+        buffers); norm = None: rows are already normalised."""
         B, Ll, nh, d = self.shape
         pl = self.pl
-        with ops.timed("sp_a2a_qkv"):
-            ops.sp_scatter_qkv(qkv, self.kv_ptrs, self.q_ptrs, B=B, Ll=Ll, heads=nh, P=pl.world, rank=pl.rank, hg=pl.hg)
-            self.barrier()
-        return (self.q_recv.view(len(pl.q_sources) * Ll, B, pl.hp, d), self.kv_recv.view(pl.world * Ll, B, 2, pl.hp, d))
+        kw = dict(B=B, Ll=Ll, heads=nh, P=pl.world, rank=pl.rank, hg=pl.hg, b_first=b_first, b_count=b_count)
+        if norm is None:
+            ops.sp_scatter_qkv(qkv, self.kv_ptrs, self.q_ptrs, **kw)
+        else:
+            wq, wk, freqs, grid, tok0 = norm
+            ops.sp_norm_rope_scatter(qkv, wq, wk, self.kv_ptrs, self.q_ptrs, freqs=freqs, grid=grid, tok_offset=tok0, **kw)
 
-    def norm_rope_exchange_qkv(self, qkv, weight_q, weight_k, freqs, grid, tok_offset):
-        """exchange_qkv with the RMSNorm + RoPE of q / k fused into the scatter: qkv holds the raw projection rows, the
-        normalised values only ever exist in the receive buffers."""
+    def scatter_o(self, b_first=0, b_count=0):
         B, Ll, nh, d = self.shape
         pl = self.pl
-        with ops.timed("sp_a2a_qkv"):
-            ops.sp_norm_rope_scatter(qkv, weight_q, weight_k, self.kv_ptrs, self.q_ptrs, B=B, Ll=Ll, heads=nh, P=pl.world,
-                                     rank=pl.rank, hg=pl.hg, freqs=freqs, grid=grid, tok_offset=tok_offset)
-            self.barrier()
-        return (self.q_recv.view(len(pl.q_sources) * Ll, B, pl.hp, d), self.kv_recv.view(pl.world * Ll, B, 2, pl.hp, d))
+        ops.sp_scatter_o(self.o_send, self.o_ptrs, B=B, Ll=Ll, heads=nh, P=pl.world, rank=pl.rank, hg=pl.hg,
+                         b_first=b_first, b_count=b_count)
 
-    def exchange_out(self, O):
-        B, Ll, nh, d = self.shape
-        pl = self.pl
-        with ops.timed("sp_a2a_o"):
-            ops.sp_scatter_o(O, self.o_ptrs, B=B, Ll=Ll, heads=nh, P=pl.world, rank=pl.rank, hg=pl.hg)
-            self.barrier()
-        return self.o_recv.view(B, Ll, nh, d)
+    def attention(self, qkv, norm, pipelined=True):
+        """Exchange + attention + exchange back for one block; returns o_recv [B, Ll, nh, d]."""
+        B = self.shape[0]
+        K, V = self.kv_recv[:, :, 0], self.kv_recv[:, :, 1]
+        if not pipelined or B == 1:
+            with ops.timed("sp_a2a_qkv"):
+                self.scatter_qkv(qkv, norm)
+                self.barrier(0)
+            with ops.timed("self_attn"):
+                ops.flash_attn(self.q_recv, K, V, out=self.o_send)
+            with ops.timed("sp_a2a_o"):
+                self.scatter_o()
+                self.barrier(0)
+            return self.o_recv
+        main = torch.cuda.current_stream(self.device)
+        with ops.timed("sp_attn_region"):
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self.comm.wait_event(fork)
+            ready = []
+            with torch.cuda.stream(self.comm):
+                for b in range(B):
+                    self.scatter_qkv(qkv, norm, b, 1)
+                    self.barrier(1)
+                    ev = torch.cuda.Event()
+                    ev.record(self.comm)
+                    ready.append(ev)
+            for b in range(B):
+                sb = self.sample_streams[b]
+                sb.wait_event(ready[b])
+                with torch.cuda.stream(sb):
+                    ops.flash_attn(self.q_recv[b:b + 1], K[b:b + 1], V[b:b + 1], out=self.o_send[b:b + 1])
+                    self.scatter_o(b, 1)
+                    ev = torch.cuda.Event()
+                    ev.record(sb)
+                main.wait_event(ev)
+            self.barrier(0)
+        return self.o_recv
 
 
-def _fused_norm():
-    """RMSNorm + RoPE of q / k fused into the peer scatter (sa_sp_norm_rope_scatter); SA_SP_FUSED_NORM=0 keeps them apart."""
-    import os
-    return os.environ.get("SA_SP_FUSED_NORM", "1") != "0"
+def _probe_peer(model, device):
+    """Can this group use the peer-store exchange? Every rank must be a CUDA device of one NCCL group with working CUDA
+    IPC + P2P towards every other rank; the ranks agree on the answer (all_reduce MIN) so nobody takes a different path."""
+    ok = device.type == "cuda" and dist.get_backend(model.sp_group) == "nccl"
+    if not ok:
+        return False
+    good = 1
+    try:
+        probe = torch.zeros(64, device=device, dtype=torch.int32)
+        metas = [None] * model.sp_world_size
+        dist.all_gather_object(metas, ops.ipc_export(probe), group=model.sp_group)
+        with torch.cuda.device(device):
+            for r, (handle, off) in enumerate(metas):
+                if r != model.sp_world_rank:
+                    ops.ipc_close(ops.ipc_open(handle))
+    except Exception:  # noqa: BLE001  (no P2P / IPC, e.g. expandable_segments allocations or ranks on different nodes)
+        good = 0
+    flag = torch.tensor([good], device=device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=model.sp_group)
+    return bool(flag.item())
 
 
 def _peer_exchange(model, B, Ll, nh, d, device):
-    """The model's PeerExchange for these shapes, or None when the NCCL path is selected (SA_SP_PEER=0, CPU / gloo)."""
-    import os
-    if device.type != "cuda" or os.environ.get("SA_SP_PEER", "1") == "0" or dist.get_backend(model.sp_group) != "nccl":
+    """The model's PeerExchange for these shapes, or None for the NCCL all_to_all_single path. model.sp_exchange:
+    "auto" (default: peer stores when the probe succeeds on every rank, else NCCL), "peer" (raise if unavailable), "nccl"."""
+    mode = getattr(model, "sp_exchange", "auto")
+    if mode == "nccl" or device.type != "cuda":
+        return None
+    ok = getattr(model, "_sp_peer_ok", None)
+    if ok is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("sequence_parallel: the first sequence-parallel forward must run eagerly (it probes and "
+                               "maps the peer buffers) before CUDA-graph capture")
+        ok = model._sp_peer_ok = _probe_peer(model, device)
+    if not ok:
+        if mode == "peer":
+            raise RuntimeError("sequence_parallel: sp_exchange='peer' but CUDA IPC / P2P is not available on every rank")
         return None
     px = getattr(model, "_sp_px", None)
     if px is None or px.shape != (B, Ll, nh, d):
@@ -286,21 +355,20 @@ def self_attention(model, qkv, sa, st):
     B, C, nh, Ll = st["B"], st["C"], st["nh"], st["Ll"]
     pl = model._sp
     px = _peer_exchange(model, B, Ll, nh, 128, qkv.device)
-    if px is not None and _fused_norm():
-        Q, KV = px.norm_rope_exchange_qkv(qkv, sa.norm_q.weight, sa.norm_k.weight, st["freqs"], st["grid"], st["tok0"])
-    else:
-        ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
-                          grid=st["grid"], rows_per_batch=Ll, tok_offset=st["tok0"])
-        if px is not None:
-            Q, KV = px.exchange_qkv(qkv)
-        else:
-            q5 = qkv.view(B, Ll, 3, nh, 128)
-            Q, KV = exchange_qkv(pl, q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], model.sp_group, kv=q5[:, :, 1:3])
+    if px is not None:
+        norm = (sa.norm_q.weight, sa.norm_k.weight, st["freqs"], st["grid"], st["tok0"])
+        if not getattr(model, "sp_fused_norm", True):        # test knob: norm in place, then the plain scatter
+            ops.rmsnorm_rope_(qkv[:, :C], norm[0], qkv[:, C:2 * C], norm[1], freqs=norm[2], grid=norm[3],
+                              rows_per_batch=Ll, tok_offset=norm[4])
+            norm = None
+        return px.attention(qkv, norm, pipelined=getattr(model, "sp_pipelined", True))
+    ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
+                      grid=st["grid"], rows_per_batch=Ll, tok_offset=st["tok0"])
+    q5 = qkv.view(B, Ll, 3, nh, 128)
+    Q, KV = exchange_qkv(pl, q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], model.sp_group, kv=q5[:, :, 1:3])
     with ops.timed("self_attn"):
         O = ops.flash_attn(Q.transpose(0, 1), KV[:, :, 0].transpose(0, 1), KV[:, :, 1].transpose(0, 1),
                            out=torch.empty_like(Q).transpose(0, 1))
-    if px is not None:
-        return px.exchange_out(O.transpose(0, 1))
     return exchange_out(pl, O.transpose(0, 1), B, Ll, nh, 128, model.sp_group)
 
 

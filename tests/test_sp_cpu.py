@@ -74,10 +74,11 @@ def test_plan_head_groups_and_query_splits():
     assert (p.hg, p.qs, p.hp) == (8, 1, 5)
 
 
-@pytest.mark.parametrize("P,nh", [(2, 12), (4, 12), (8, 12), (8, 40), (8, 4)])
+@pytest.mark.parametrize("P,nh", [(2, 12), (4, 12), (8, 12), (8, 40), (2, 40), (8, 4)])
 def test_peer_scatter_index_math_gives_the_all_to_all_layout(P, nh):
-    """csrc/sp_exchange.cu's destination arithmetic, restated in numpy on tagged 16-byte chunks: after every rank's
-    scatter each rank holds K/V of its head group for ALL tokens (token-major, source-rank order), Q for its query
+    """csrc/sp_exchange.cu's destination arithmetic, restated in numpy on tagged 16-byte chunks and driven sample by
+    sample like the pipelined exchange (b_first, b_count = b, 1): after every rank's scatters each rank holds K/V of its
+    head group for ALL tokens ([B, source rank, Ll], i.e. batch-outermost with a uniform token stride), Q for its query
     split, and after the O scatter every rank holds [B, Ll, heads] with each head group written by its owner."""
     import math
     import numpy as np
@@ -87,42 +88,46 @@ def test_peer_scatter_index_math_gives_the_all_to_all_layout(P, nh):
     qs, hp = P // hg, nh // hg
     n_src = P // qs
     qkv = [(np.arange(B * Ll * 3 * nh * 16) + r * 10 ** 6).reshape(B, Ll, 3, nh, 16) for r in range(P)]
-    kv_recv = [np.full(P * Ll * B * 2 * hp * 16, -1) for _ in range(P)]
-    q_recv = [np.full(n_src * Ll * B * hp * 16, -1) for _ in range(P)]
-    for rank in range(P):                                        # scatter_qkv_kernel
+    kv_recv = [np.full(B * P * Ll * 2 * hp * 16, -1) for _ in range(P)]
+    q_recv = [np.full(B * n_src * Ll * hp * 16, -1) for _ in range(P)]
+    for rank in range(P):                                        # scatter_qkv_kernel, one launch per sample
         src = qkv[rank].reshape(B * Ll, 3 * nh * 16)
-        for e in range(3 * nh * 16):
-            c, h, which = e & 15, (e >> 4) % nh, (e >> 4) // nh
-            g, hl = h // hp, h % hp
-            for bt in range(B * Ll):
-                t, b = bt % Ll, bt // Ll
-                if which == 0:
-                    q_recv[g * qs + rank % qs][(((rank // qs) * Ll + t) * B + b) * (hp * 16) + hl * 16 + c] = src[bt, e]
-                else:
-                    off = ((rank * Ll + t) * B + b) * (2 * hp * 16) + ((which - 1) * hp + hl) * 16 + c
-                    for s in range(qs):
-                        kv_recv[g * qs + s][off] = src[bt, e]
+        for b_first in range(B):
+            for e in range(3 * nh * 16):
+                c, h, which = e & 15, (e >> 4) % nh, (e >> 4) // nh
+                g, hl = h // hp, h % hp
+                for bt in range(1 * Ll):
+                    t, b = bt % Ll, b_first + bt // Ll
+                    val = src[b_first * Ll + bt, e]
+                    if which == 0:
+                        q_recv[g * qs + rank % qs][((b * n_src + rank // qs) * Ll + t) * (hp * 16) + hl * 16 + c] = val
+                    else:
+                        off = ((b * P + rank) * Ll + t) * (2 * hp * 16) + ((which - 1) * hp + hl) * 16 + c
+                        for s in range(qs):
+                            kv_recv[g * qs + s][off] = val
     for r in range(P):
         g, pl = r // qs, sp.plan(nh, P, r)
-        KV = kv_recv[r].reshape(P, Ll, B, 2, hp, 16)
-        Q = q_recv[r].reshape(n_src, Ll, B, hp, 16)
+        KV = kv_recv[r].reshape(B, P, Ll, 2, hp, 16)
+        Q = q_recv[r].reshape(B, n_src, Ll, hp, 16)
         for s_r in range(P):
-            want = qkv[s_r][:, :, 1:3, g * hp:(g + 1) * hp].transpose(1, 0, 2, 3, 4)          # [Ll, B, 2, hp, 16]
-            assert (KV[s_r] == want).all()
+            assert (KV[:, s_r] == qkv[s_r][:, :, 1:3, g * hp:(g + 1) * hp]).all()             # [B, Ll, 2, hp, 16]
         for i, s_r in enumerate(pl.q_sources):
-            assert (Q[i] == qkv[s_r][:, :, 0, g * hp:(g + 1) * hp].transpose(1, 0, 2, 3)).all()
-    o_loc = [(np.arange(n_src * Ll * B * hp * 16) + r * 10 ** 6).reshape(n_src, Ll, B, hp, 16) for r in range(P)]
+            assert (Q[:, i] == qkv[s_r][:, :, 0, g * hp:(g + 1) * hp]).all()
+    o_loc = [(np.arange(B * n_src * Ll * hp * 16) + r * 10 ** 6).reshape(B, n_src, Ll, hp, 16) for r in range(P)]
     o_recv = [np.full(B * Ll * nh * 16, -1) for _ in range(P)]
-    for rank in range(P):                                        # scatter_o_kernel
+    for rank in range(P):                                        # scatter_o_kernel, one launch per sample
         cols, g = hp * 16, rank // qs
-        flat = o_loc[rank].reshape(-1, cols)
-        for row in range(n_src * Ll * B):
-            b, lt = row % B, row // B
-            t, src = lt % Ll, lt // Ll
-            base = (b * Ll + t) * (nh * 16) + g * cols
-            o_recv[src * qs + rank % qs][base:base + cols] = flat[row]
+        flat = o_loc[rank].reshape(-1)
+        rows_b = n_src * Ll
+        for b_first in range(B):
+            for idx in range(1 * rows_b * cols):
+                row, col = idx // cols, idx % cols
+                bl, lt = row // rows_b, row % rows_b
+                src, t = lt // Ll, lt % Ll
+                b = b_first + bl
+                o_recv[src * qs + rank % qs][(b * Ll + t) * (nh * 16) + g * cols + col] = flat[(b * rows_b + lt) * cols + col]
     for r in range(P):
         O = o_recv[r].reshape(B, Ll, nh, 16)
         for g in range(hg):
             owner = g * qs + r % qs
-            assert (O[:, :, g * hp:(g + 1) * hp] == o_loc[owner][r // qs].transpose(1, 0, 2, 3)).all()
+            assert (O[:, :, g * hp:(g + 1) * hp] == o_loc[owner][:, r // qs]).all()
