@@ -89,27 +89,46 @@ def step_flops(cfg, L, B=3, text=512, clip=257, G=21, A=15):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
-def cpu_block_sample(cfg, L, grid, threads=None):
-    """Time ONE WanAttentionBlock of the oracle (CPU restatement of 1B.py:650-695) at the full sequence length, B=1."""
+def host_threads():
+    """All host threads for the CPU arm: torchrun exports OMP_NUM_THREADS=1, which would make the reference arm 12x slower
+    than the same code launched directly (round-1 SCALE ratios were inflated by exactly that)."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except AttributeError:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_block_case(cfg, L, grid):
+    """Weights and inputs of ONE WanAttentionBlock at the full sequence length, B=1 (bf16-representable values, so the
+    B200 block can be run on exactly the same numbers)."""
     from oracle import dit as O
     from stableavatar_b200 import synth
-    if threads:
-        torch.set_num_threads(threads)
     one = dict(cfg, num_layers=1)
     shapes = {k: v for k, v in synth.dit_param_shapes(one).items() if k.startswith("blocks.0.")}
     g = torch.Generator().manual_seed(0)
-    sd = {k: torch.randn(v, generator=g) * (0.02 if len(v) < 2 or k.endswith("bias") else v[-1] ** -0.5) for k, v in shapes.items()}
+    r = lambda t: t.bfloat16().float()  # noqa: E731
+    sd = {k: r(torch.randn(v, generator=g) * (0.02 if len(v) < 2 or k.endswith("bias") else v[-1] ** -0.5)) for k, v in shapes.items()}
+    for k in list(sd):
+        if k.endswith("norm_q.weight") or k.endswith("norm_k.weight") or k.endswith("norm_k_img.weight") or k.endswith("norm3.weight"):
+            sd[k] = r(1.0 + 5.0 * sd[k])                      # norm scales around 1
     d = cfg["dim"]
-    x = torch.randn(1, L, d, generator=g)
-    e0 = torch.randn(1, 6, d, generator=g) * 0.1
-    ctx = torch.randn(1, 257 + 512, d, generator=g)
     G = grid[0]
-    vc = torch.randn(1, G, 15, d, generator=g)
-    freqs = O.rope_freqs(d // cfg["num_heads"])
+    return dict(sd=sd, x=r(torch.randn(1, L, d, generator=g)), e0=r(torch.randn(1, 6, d, generator=g) * 0.1),
+                ctx=r(torch.randn(1, 257 + 512, d, generator=g)), vc=r(torch.randn(1, G, 15, d, generator=g)), grid=grid, G=G,
+                freqs=O.rope_freqs(d // cfg["num_heads"]), heads=cfg["num_heads"])
+
+
+def cpu_block_run(case):
+    """Time the oracle block (CPU restatement of 1B.py:650-695) on `case`; returns (seconds, output [1, L, C])."""
+    from oracle import dit as O
     t0 = time.perf_counter()
     with torch.no_grad():
-        O.dit_block(sd, "blocks.0.", x, e0, [grid], freqs, ctx, vc, G, cfg["num_heads"])
-    return time.perf_counter() - t0
+        out = O.dit_block(case["sd"], "blocks.0.", case["x"], case["e0"], [case["grid"]], case["freqs"], case["ctx"], case["vc"],
+                          case["G"], case["heads"])
+    return time.perf_counter() - t0, out
 
 
 def run_reference(args):
@@ -122,19 +141,20 @@ def run_reference(args):
     from stableavatar_b200 import synth
     cfg = synth.DIT_1_3B
     F_lat, h, w, L = workload(args)
-    cores = torch.get_num_threads()
+    cores = host_threads()
     steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    case = cpu_block_case(cfg, L, (F_lat, h // 2, w // 2))
     for _ in range(warm):
-        cpu_block_sample(cfg, L, (F_lat, h // 2, w // 2))
-    ts = [cpu_block_sample(cfg, L, (F_lat, h // 2, w // 2)) for _ in range(steps)]
+        cpu_block_run(case)
+    ts = [cpu_block_run(case)[0] for _ in range(steps)]
     per_block = sum(ts) / len(ts)
     value = per_block * cfg["num_layers"] * 3
-    sample = (f"1 WanAttentionBlock (oracle port, fp32) at L={L}, B=1: {per_block:.2f} s measured; "
+    sample = (f"1 WanAttentionBlock (oracle port, fp32) at L={L}, B=1: {per_block:.2f} s measured on {cores} threads; "
               f"x{cfg['num_layers']} blocks x3 CFG samples extrapolated; {steps} timed / {warm} warm-up samples")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"1.3B audio-DiT denoise step, {args.height}x{args.width}x{args.frames}f, CFG batch 3, L={L}"},
+            "config": {"workload": workload_name(args, L)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -156,6 +176,24 @@ def build_model(cfg, device):
     return m.init_random_(seed=0)
 
 
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def gpu_block_parity(cfg, case, dev):
+    """The B200 WanAttentionBlock at the benchmarked size (dim 1536, ffn 8960, L = 32 760, B = 1) on the weights and inputs
+    of the CPU-baseline sample -> [1, L, C] for the comparison with the oracle output (north_star: <= 2e-2 per block)."""
+    one = dict(cfg, num_layers=1)
+    m = build_model(one, dev)
+    own = m.state_dict()
+    own.update({k: v.to(dev, torch.bfloat16) for k, v in case["sd"].items()})
+    m.load_state_dict(own, strict=True)
+    out = m.block_forward(0, case["x"].to(dev), case["e0"].to(dev), case["ctx"].to(dev), case["vc"].to(dev), case["grid"])
+    torch.cuda.synchronize()
+    return out.float().cpu()
+
+
 def run_b200(args):
     import torch.distributed as dist
     from stableavatar_b200 import _lib as L_, ops, synth
@@ -169,11 +207,10 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        ops.sp_set_barrier_timeout_ms(120_000)      # the ranks of a bench run enter every forward together
     cfg = synth.DIT_1_3B
     F_lat, h, w, L = workload(args)
     model = build_model(cfg, dev)
-    if world > 1:
-        model.enable_multi_gpus_inference()
     sched = FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=5.0)
     sched.set_timesteps(50, device=dev)
     pipe = WanI2VTalkingInferenceLongPipeline(transformer=model, scheduler=sched)
@@ -204,6 +241,29 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     resident = to_dev()
+
+    # ---- multi-GPU parity, driver-visible: the sequence-parallel forward against the single-GPU forward of the same
+    # inputs on every rank (the single-GPU semantics are the oracle of the SP path), max over ranks
+    sp_parity = None
+    if world > 1:
+        kw = dict(x=resident["latents"].expand(3, -1, -1, -1, -1).contiguous(), t=torch.full((3,), 900.0, device=dev),
+                  context=resident["ctx"], seq_len=L, clip_fea=resident["clip"], y=resident["y"],
+                  vocal_embeddings=resident["audio"], video_sample_n_frames=args.frames)
+        single = model(**kw).float()
+        model.enable_multi_gpus_inference()
+        sp_out = model(**kw).float()
+        torch.cuda.synchronize()
+        err = torch.tensor([rel_l2(sp_out, single)], device=dev)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        sp_parity = err.item()
+        del single, sp_out, kw
+        if not (sp_parity <= 1e-2):
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "sequence-parallel forward differs from the single-GPU forward",
+                                  "sp_parity_rel_l2": sp_parity, "n_gpus": world}), flush=True)
+            dist.destroy_process_group()
+            raise SystemExit(3)
+
     for i in range(args.warmup):
         step(resident, i)
     barrier()
@@ -227,27 +287,41 @@ def run_b200(args):
     clocks = sampler.summary() if sampler else None
 
     # ---- instrumented pass: the same K steps launched eagerly, with CUDA events around the dominant kernels on the
-    # launching stream (events cannot be read back from inside a replayed graph) and the launch counter running
-    pipe.use_cuda_graphs = False
-    ops.TIMING = {}
-    L_.launch_count = 0
-    ei0, ei1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ei0.record()
-    for i in range(args.steps):
-        step(resident, i)
-    ei1.record()
-    barrier()
-    launches = L_.launch_count
-    timing, ops.TIMING = ops.TIMING, None
-    ms_eager = ei0.elapsed_time(ei1)
+    # launching stream (events cannot be read back from inside a replayed graph) and the launch counter running.
+    # Under sequence parallelism the product path pipelines the exchange under the attention of the neighbouring CFG
+    # samples (one "sp_attn_region" per block); a second pass with the pipeline off times attention and the two
+    # exchanges on their own, so that exposed = region - attention can be reported.
+    def instrumented():
+        ops.TIMING = {}
+        L_.launch_count = 0
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for i in range(args.steps):
+            step(resident, i)
+        b.record()
+        barrier()
+        timing, ops.TIMING = ops.TIMING, None
+        total = a.elapsed_time(b)
+        return total, {k: sum(x.elapsed_time(y) for x, y in v) for k, v in timing.items()}, \
+            {k: len(v) for k, v in timing.items()}, L_.launch_count
 
-    # ---- timed region 2: end to end through the pipeline API with host buffers ("e2e"); the pipeline's default path
-    # replays one captured CUDA graph per step
+    pipe.use_cuda_graphs = False
+    ms_eager, tag_ms, tag_n, launches = instrumented()
+    serial = None
+    if world > 1:
+        model.sp_pipelined = False
+        ms_serial, s_ms, s_n, _ = instrumented()
+        model.sp_pipelined = True
+        serial = dict(total=ms_serial, ms=s_ms, n=s_n)
+
+    # ---- timed region 2: end to end through the pipeline API with host buffers ("e2e"): every step copies its inputs
+    # from pinned host memory, runs the captured step (the conditioning changed, so the context is re-encoded) and reads
+    # the result back
     pipe.use_cuda_graphs = not args.no_graph
     staged = to_dev()
     for i in range(2):
-        step(staged, i)                                      # capture + one replay, untimed
+        step(staged, i)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -268,17 +342,21 @@ def run_b200(args):
     s_per_step = ms.item() / 1e3 / args.steps
     s_e2e = ms_e2e.item() / 1e3 / args.steps
 
-    def vae_decode_time():
-        """BASELINE "e2e s/clip": the clip = 50 denoise steps + one Wan VAE decode of the final latents (pipe.py:793-799).
-        One GPU: plain decode. N > 1: the decoder runs as a pipeline over the N ranks (bit-identical frames,
-        AutoencoderKLWan.enable_multi_gpus_decode); time = max over ranks."""
+    extras = {"vae_decode_s": None, "vae_pp_equal": None, "clip_s": None}
+
+    def vae_stage():
+        """Config 4: one Wan VAE decode of the final latents (pipe.py:793-799). One GPU: plain decode. N > 1: the decoder
+        runs as a pipeline over the N ranks (AutoencoderKLWan.enable_multi_gpus_decode) and its frames are compared
+        bit for bit with the single-GPU decode of the same latents on every rank; time = max over ranks."""
         from stableavatar_b200.wan_vae import AutoencoderKLWan
         vae = AutoencoderKLWan()
-        vae.load_state_dict(synth.vae_state_dict(), strict=True)
+        vae.load_state_dict(synth.vae_state_dict(encoder=True), strict=True)
         vae = vae.to(dev)
-        if world > 1:
-            vae.enable_multi_gpus_decode()
         z = synth.det_normal("bench_z", (1, 16, F_lat, h, w)).to(dev)
+        single = None
+        if world > 1:
+            single = vae.decode(z).sample
+            vae.enable_multi_gpus_decode()
         vae.decode(z[:, :, :2])                              # warm-up: operand preparation
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -289,77 +367,144 @@ def run_b200(args):
         assert video.shape == (1, 3, args.frames, args.height, args.width)
         tv = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
         if world > 1:
+            same = torch.tensor([int(torch.equal(video, single))], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
             dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-        return tv.item() / 1e3
+            extras["vae_pp_equal"] = bool(same.item())
+        extras["vae_decode_s"] = tv.item() / 1e3
+        del video, single
+        return vae
 
-    def emit(vae_s):
+    def clip_stage(vae):
+        """BASELINE "e2e s/clip", measured: ONE call of the reference entry point `pipe(...)` with pre-encoded prompt /
+        CLIP / audio features (the encoders are outside the path): VAE encode of the conditioning clip, mask / y
+        assembly, 50 denoise steps with 3-way CFG, VAE decode, the 388 MB fp32 read-back of decode_latents. Wall clock
+        between synchronised barriers, max over ranks."""
+        pipe.vae = vae
+        gen = torch.Generator(device=dev).manual_seed(0)
+        pos, neg = host["ctx"][2].to(dev), host["ctx"][0].to(dev)
+        audio = resident["audio"][1:2]
+        cond = synth.det_normal("bench_cond_image", (1, 3, 1, args.height, args.width)).clamp_(-1, 1)
+        kw = dict(height=args.height, width=args.width, num_frames=args.frames, clip_length=args.frames, guidance_scale=6.0,
+                  text_guide_scale=3.0, audio_guide_scale=5.0, generator=gen, prompt_embeds=[pos], negative_prompt_embeds=[neg],
+                  clip_context=resident["clip"][:1], cond_image=cond, vocal_input_values=torch.zeros(args.frames * 640),
+                  sr=16000, fps=25, vocal_embeddings_fn=lambda ws, we, last: audio, overlap_window_length=5)
+        pipe(num_inference_steps=1, **kw)                    # warm-up: VAE encode operand preparation
+        barrier()
+        t0 = time.perf_counter()
+        video = pipe(num_inference_steps=args.clip_steps, **kw).videos
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert tuple(video.shape) == (1, 3, args.frames, args.height, args.width) and bool(torch.isfinite(video).all())
+        extras["clip_s"] = dt.item()
+
+    def emit():
         if rank == 0:
-            line["config"]["vae_decode_s"] = vae_s
-            line["config"]["clip_s"] = None if vae_s is None else 50 * s_per_step + vae_s
+            c = line["config"]
+            c["vae_decode_s"], c["clip_s"] = extras["vae_decode_s"], extras["clip_s"]
+            c["clip_s_model"] = None if extras["vae_decode_s"] is None else 50 * s_per_step + extras["vae_decode_s"]
+            if world > 1:
+                line["vae_pp_equal"] = extras["vae_pp_equal"]
             print(json.dumps(line), flush=True)
 
     if rank == 0:
         peaks = load_peaks()
         total_flops, attn_flops_per_launch = step_flops(cfg, L)
-        attn_ms = [a.elapsed_time(b) for a, b in timing.get("self_attn", [])]
-        attn_avg = sum(attn_ms) / max(1, len(attn_ms))
-        achieved = attn_flops_per_launch / world / (attn_avg * 1e-3) / 1e12 if attn_ms else None
-        shares = {k: sum(a.elapsed_time(b) for a, b in v) / ms_eager for k, v in timing.items()}
+        src = serial if serial is not None else dict(total=ms_eager, ms=tag_ms, n=tag_n)
+        n_attn = src["n"].get("self_attn", 0)
+        attn_avg = src["ms"].get("self_attn", 0.0) / max(1, n_attn)
+        achieved = attn_flops_per_launch / world / (attn_avg * 1e-3) / 1e12 if n_attn else None
+        shares = {k: v / ms_eager for k, v in tag_ms.items()}
+        shares["other"] = max(0.0, 1.0 - sum(shares.values()))
         line = {
             "metric": METRIC, "value": s_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"1.3B audio-DiT denoise step (30 blocks, CFG batch 3 + CFG/Euler), "
-                                   f"{args.height}x{args.width}x{args.frames}f, L={L}, text 512 + CLIP 257 + audio 21x15",
+            "config": {"workload": workload_name(args, L),
+                       "detail": "30 blocks, CFG batch 3 + CFG/Euler, text 512 + CLIP 257 + audio 21x15; text/CLIP context encoded "
+                                 "once per clip (value) / once per step (e2e: its inputs change every step)",
                        "parallelism": f"sp{world}" if world > 1 else "single",
                        "l2_policy": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
                        "step_tflop": total_flops / 1e12,
                        "step_tflops_achieved": total_flops / s_per_step / 1e12 / world,
                        "bf16_peak_frac_step": total_flops / s_per_step / 1e12 / world / peaks["bf16"],
-                       "launch_mode": "eager" if args.no_graph else "cuda-graph replay (value, e2e; under sequence parallelism the self-attention exchange is peer-store "
-                                      "kernels inside the graph, one eager NCCL all-gather per step); kernel timing and "
-                                      "gpu_launches from an eager pass of the same steps",
+                       "launch_mode": "eager" if args.no_graph else "cuda-graph replay (value, e2e; under sequence parallelism the self-attention "
+                                      "exchange is peer-store kernels on side streams inside the graph, one eager NCCL all-gather per step); "
+                                      "kernel timing and gpu_launches from an eager pass of the same steps",
                        "eager_ms_per_step": ms_eager / args.steps, "kernel_time_share": shares,
-                       "vae_decode_s": None, "clip_s": None,
-                       "clip_s_note": "50 denoise steps x value + one VAE decode (21x60x104 latent -> 81x480x832)"
-                                      + (f", decoder pipelined over the {world} GPUs (bit-identical frames)" if world > 1 else "")},
+                       "vae_decode_s": None, "clip_s": None, "clip_s_model": None,
+                       "clip_s_note": f"clip_s = one measured pipe(...) call: VAE encode of the conditioning clip + {args.clip_steps} denoise steps + "
+                                      "VAE decode + fp32 read-back (wall clock, max over ranks); clip_s_model = 50 x value + vae_decode_s"
+                                      + (f"; decoder pipelined over the {world} GPUs" if world > 1 else "")},
             "roofline": {"kernel": "attn8::flash_attn_v8_kernel (self-attention, sa_flash_attn_d128)", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"] if achieved else None,
-                         "traffic": SELF_ATTN_DRAM_BYTES_B3 / world if (args.frames, args.height, args.width) == (81, 480, 832) else None,
+                         "traffic": SELF_ATTN_DRAM_BYTES_B3 if (world == 1 and (args.frames, args.height, args.width) == (81, 480, 832)) else None,
                          "traffic_source": "profiles/r01_selfattn_in_bench_ncu.txt (ncu --set full, dram__bytes_read+write of one "
-                                           "B=3 self-attention launch; algorithmic q+k+v+o = 1208 MB)",
+                                           "B=3 self-attention launch; algorithmic q+k+v+o = 1208 MB); null at N > 1 (ncu is single-GPU only "
+                                           "and the 4x2 split at N = 8 reads each K/V chunk on two ranks)",
                          "peak_source": f"{peaks['src']} sustained bf16 (MEASURED_PEAKS.json)",
-                         "launches_timed": len(attn_ms), "avg_launch_ms": attn_avg},
+                         "launches_timed": n_attn, "avg_launch_ms": attn_avg,
+                         "timed_in": "eager pass, exchange pipeline off" if serial is not None else "eager pass"},
             "e2e": {"value": s_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_host.numel() * 2},
             "gpu_launches": launches, "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            cores = torch.get_num_threads()
-            per_block = cpu_block_sample(cfg, L, (F_lat, h // 2, w // 2))
-            line["cpu_baseline"] = {"value": per_block * cfg["num_layers"] * 3, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"1 WanAttentionBlock of the oracle port (fp32) at L={L}, B=1 measured "
-                                              f"{per_block:.2f} s; extrapolated x{cfg['num_layers']} blocks x3 CFG samples"}
-    # The VAE stage runs last and under a watchdog: if the multi-GPU decode does not finish, the step line is still printed.
+        if world > 1:
+            line["sp_parity_rel_l2"] = sp_parity
+            per_step = lambda d, k: d["ms"].get(k, 0.0) / args.steps  # noqa: E731
+            region = tag_ms.get("sp_attn_region", 0.0) / args.steps
+            attn = per_step(serial, "self_attn")
+            line["sp_exchange"] = {
+                "note": "per step and rank, ms. serial_*: exchange pipeline off (scatter + barrier timed alone); region_pipelined: "
+                        "fork -> exchange || attention per CFG sample -> join + barrier, as shipped; exposed = region - attention",
+                "serial_qkv_ms": per_step(serial, "sp_a2a_qkv"), "serial_o_ms": per_step(serial, "sp_a2a_o"), "attention_ms": attn,
+                "region_pipelined_ms": region, "exposed_ms": region - attn,
+                "exposed_share_of_step": (region - attn) / (ms_eager / args.steps),
+                "eager_ms_per_step_serial": serial["total"] / args.steps}
+    case = None
+    if world == 1 and not args.no_cpu_baseline:
+        # CPU baseline: one oracle block at the full sequence length on all host threads — and the same block on the B200
+        # on the same numbers: parity at the benchmarked size
+        cores = host_threads()
+        case = cpu_block_case(cfg, L, (F_lat, h // 2, w // 2))
+        per_block, ref_out = cpu_block_run(case)
+        line["cpu_baseline"] = {"value": per_block * cfg["num_layers"] * 3, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"1 WanAttentionBlock of the oracle port (fp32) at L={L}, B=1 measured "
+                                          f"{per_block:.2f} s on {cores} threads; extrapolated x{cfg['num_layers']} blocks x3 CFG samples"}
+        gpu_out = gpu_block_parity(cfg, case, dev)
+        line["block_parity_rel_l2"] = rel_l2(gpu_out, ref_out)
+        line["block_parity_note"] = ("B200 WanAttentionBlock vs oracle block (fp32 CPU) on the same bf16-representable weights and "
+                                     f"inputs at dim {cfg['dim']}, ffn {cfg['ffn_dim']}, L={L}, B=1; north_star bar 2e-2")
+        del gpu_out, ref_out, case
+    # The VAE and clip stages run last and under a watchdog: if one does not finish, the step line is still printed.
     if args.no_vae:
-        emit(None)
+        emit()
     else:
-        import threading
-
         def give_up():
-            emit(None)
+            emit()
             os._exit(0)
-        timer = threading.Timer(240.0, give_up)
+        timer = threading.Timer(args.stage_timeout, give_up)
         timer.daemon = True
         timer.start()
         try:
-            vae_s = vae_decode_time()
+            vae = vae_stage()
+            if not args.no_clip:
+                clip_stage(vae)
         except Exception as exc:  # noqa: BLE001
-            print(f"[bench] VAE decode stage failed on rank {rank}: {exc!r}", file=sys.stderr, flush=True)
-            vae_s = None
+            print(f"[bench] VAE / clip stage failed on rank {rank}: {exc!r}", file=sys.stderr, flush=True)
         timer.cancel()
-        emit(vae_s)
+        emit()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and "block_parity_rel_l2" in line and not (line["block_parity_rel_l2"] <= 2e-2):
+        raise SystemExit(4)
+    if world > 1 and extras["vae_pp_equal"] is False:
+        raise SystemExit(5)
+
+
+def workload_name(args, L):
+    return f"1.3B audio-DiT denoise step, {args.height}x{args.width}x{args.frames}f, CFG batch 3, L={L}"
 
 
 def main():
@@ -373,7 +518,10 @@ def main():
     ap.add_argument("--width", type=int, default=832)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="e2e region without CUDA-graph replay")
-    ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode timing that feeds config.clip_s")
+    ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode and measured-clip stages")
+    ap.add_argument("--no-clip", action="store_true", help="skip the measured pipe(...) clip (config.clip_s)")
+    ap.add_argument("--clip-steps", type=int, default=50, help="denoise steps of the measured clip")
+    ap.add_argument("--stage-timeout", type=float, default=420.0, help="watchdog for the VAE + clip stages, seconds")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -349,6 +349,15 @@ class WanTransformer3DFantasyModel(nn.Module):
         c = ops.layernorm(clip_fea.to(dev, bf).reshape(B * n_img, -1).contiguous(), weight=ip[0].weight, bias=ip[0].bias, eps=1e-5)
         c = ops.gemm(ops.gemm(c, ip[1].weight, ip[1].bias, act=ops.ACT_GELU_ERF), ip[3].weight, ip[3].bias)
         ctx_img = ops.layernorm(c, weight=ip[4].weight, bias=ip[4].bias, eps=1e-5)
+        if out is not None and out.batch != B:
+            raise RuntimeError(f"encode_context: out was built for batch {out.batch}, got {B}")
+        return self._project_context(ctx_txt, ctx_img, B, out)
+
+    def _project_context(self, ctx_txt, ctx_img, B, out=None):
+        """Per-block text / image K|V projections + RMSNorm of K (1B.py:550-554) from the embedded context rows
+        ctx_txt [B*text_len, C], ctx_img [B*257, C]."""
+        p = self._prepare()
+        C = self.dim
         kv, kvi = [], []
         for i, (blk, pb) in enumerate(zip(self.blocks, p["blocks"])):
             ca = blk.cross_attn
@@ -358,11 +367,23 @@ class WanTransformer3DFantasyModel(nn.Module):
             ops.rmsnorm_rope_(k2[:, :C], ca.norm_k_img.weight)
             kv.append(k1)
             kvi.append(k2)
-        if out is not None:
-            if out.batch != B:
-                raise RuntimeError(f"encode_context: out was built for batch {out.batch}, got {B}")
-            return out
-        return ContextCache(batch=B, kv=kv, kvi=kvi)
+        return out if out is not None else ContextCache(batch=B, kv=kv, kvi=kvi)
+
+    @torch.no_grad()
+    def block_forward(self, i, x, e0, context, vocal_context, grid):
+        """`WanAttentionBlock.forward` (1B.py:650-695) of block i on its own inputs — the per-block parity hook (tests,
+        bench.py `block_parity_rel_l2`). x [B, L, C]; e0 [B, 6, C]; context [B, 257 + text_len, C] already embedded (CLIP
+        rows, then text rows, 1B.py:544-545); vocal_context [B, G, A, C]; grid = (F, H/2, W/2) token grid."""
+        p = self._prepare()
+        bf = torch.bfloat16
+        B, L, C = x.shape
+        ctx = context.to(bf)
+        cc = self._project_context(ctx[:, 257:].reshape(-1, C).contiguous(), ctx[:, :257].reshape(-1, C).contiguous(), B)
+        e = ops.add_bcast(p["mods"], e0.to(bf).reshape(B, 6 * C).contiguous())[i]
+        vc = vocal_context.to(bf)
+        st = dict(B=B, L=L, C=C, nh=self.num_heads, G=vc.shape[1], grid=tuple(grid), freqs=self._freqs_table(x.device), ctx=cc,
+                  vc=vc.reshape(B, -1, C).contiguous(), vc_grouped=True)
+        return self._block(i, x.to(bf).reshape(B * L, C).clone(), e, st).view(B, L, C)
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()

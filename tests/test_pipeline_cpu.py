@@ -152,3 +152,80 @@ def test_oracle_pipeline_chain_vs_real_reference_pipeline(golden_dir, name):
         ref_video = torch.from_numpy(gold["video_f16"].astype(np.float32))
         mse = ((video.double() - ref_video.double()) ** 2).mean().item()
         assert 10 * math.log10(1.0 / mse) > 45.0
+
+
+# ---------------------------------------------------------------------------------------------- product host logic vs goldens
+@pytest.mark.parametrize("T,nf", [(9, 5), (17, 9), (134, 81), (161, 81), (173, 81), (161, 69)])
+def test_product_window_gather_table_vs_reference_golden(golden_dir, T, nf):
+    """The PRODUCT's audio-window index table (stableavatar_b200/vocal_projector.py: split_audio_sequence +
+    window_gather_table, what the gather kernel consumes) against the tables the REAL reference produced
+    (vocal_projector_fantasy.py:39-131, tests/golden/dit_tiny.npz written by tools/gen_golden.py)."""
+    from stableavatar_b200.vocal_projector import split_audio_sequence, window_gather_table
+    gold = np.load(golden_dir / "dit_tiny.npz")
+    ranges = split_audio_sequence(T, num_frames=nf)
+    assert np.array_equal(np.array(ranges), gold[f"win_{T}_{nf}_ranges"])
+    table, lens = window_gather_table(T, ranges, expand_length=4)
+    # golden: 1-based source index of every slot, 0 = zero padding appended at the end of the window
+    assert np.array_equal(np.array(table, dtype=np.int64) + 1, gold[f"win_{T}_{nf}_gather"])
+    assert np.array_equal(np.array(lens), gold[f"win_{T}_{nf}_lens"])
+
+
+def _bare_pipeline():
+    from stableavatar_b200.pipeline import WanI2VTalkingInferenceLongPipeline
+    return WanI2VTalkingInferenceLongPipeline()
+
+
+@pytest.mark.parametrize("kw,msg", [
+    (dict(prompt="a", height=484, width=832), "divisible by 8"),
+    (dict(prompt="a", height=480, width=832, cb=["nope"]), "callback_on_step_end_tensor_inputs"),
+    (dict(prompt="a", height=480, width=832, prompt_embeds=torch.zeros(1, 4, 8)), "Cannot forward both `prompt`"),
+    (dict(prompt=None, height=480, width=832), "Provide either `prompt` or `prompt_embeds`"),
+    (dict(prompt=3, height=480, width=832), "has to be of type `str` or `list`"),
+    (dict(prompt="a", height=480, width=832, negative_prompt_embeds=torch.zeros(1, 4, 8)), "negative_prompt_embeds"),
+    (dict(prompt=None, height=480, width=832, prompt_embeds=torch.zeros(1, 4, 8), negative_prompt="x",
+          negative_prompt_embeds=torch.zeros(1, 4, 8)), "Cannot forward both `negative_prompt`"),
+    (dict(prompt=None, height=480, width=832, prompt_embeds=torch.zeros(1, 4, 8), negative_prompt_embeds=torch.zeros(1, 5, 8)),
+     "must have the same shape"),
+    (dict(prompt="a", height=488, width=832), "divisible by 16"),
+])
+def test_check_inputs_raises_like_the_reference(kw, msg):
+    """pipe.py:458-507: same conditions, same ValueError texts."""
+    kw = dict(kw)
+    pipe = _bare_pipeline()
+    with pytest.raises(ValueError, match=msg.replace("`", ".")):
+        pipe.check_inputs(kw.pop("prompt"), kw.pop("height"), kw.pop("width"), kw.pop("negative_prompt", None),
+                          kw.pop("cb", ["latents"]), **kw)
+
+
+def test_call_validates_before_touching_the_device():
+    pipe = _bare_pipeline()
+    with pytest.raises(ValueError, match="divisible by 8"):
+        pipe(prompt="a", height=481, width=832)
+    with pytest.raises(NotImplementedError, match="offload"):
+        pipe.enable_model_cpu_offload(device="cuda")
+
+
+def test_pipeline_to_moves_modules_and_returns_self():
+    """`pipeline.to(device=device)` (inference.py:524)."""
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(2))
+    from stableavatar_b200.pipeline import WanI2VTalkingInferenceLongPipeline
+    mods = dict(text_encoder=M(), vae=M(), transformer=M(), clip_image_encoder=M())
+    pipe = WanI2VTalkingInferenceLongPipeline(tokenizer=object(), wav2vec=M(), **mods)
+    assert pipe.to(device="cpu") is pipe and pipe.to("cpu") is pipe
+    pipe.to(torch.float64)
+    assert pipe.transformer.p.dtype == torch.float64 and pipe.vae.p.dtype == torch.float32
+
+
+def test_dsigma_falls_back_to_a_sigma_table():
+    """A scheduler without the repo's dsigma_at (e.g. diffusers' own class, as inference.py passes) still works."""
+    from stableavatar_b200.pipeline import _dsigma_at
+    s = FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=5.0)
+    s.set_timesteps(10, device="cpu", mu=1)
+
+    class Foreign:
+        sigmas = s.sigmas
+    for i in range(10):
+        assert _dsigma_at(Foreign(), i) == s.dsigma_at(i)

@@ -74,6 +74,21 @@ def test_decode_is_idempotent_across_calls(vae):
     assert torch.equal(a, b)
 
 
+def test_benchmark_grid_vs_real_reference_subsample(vae, golden_dir):
+    """SURVEY.md §8c pin #4: the decode at the BENCHMARK's latent grid — z [1,16,3,60,104] -> [1,3,9,480,832], the conv
+    shapes of config 4 (96->96 @480x832, 192->192 @240x416 ...) — against the REAL reference's output, kept as every 8th
+    row / column (tools/gen_golden_vae.py gen_vae_fullres) plus per-frame first and second moments of all pixels."""
+    gold = np.load(golden_dir / "vae_fullres_sub.npz")
+    z = synth.det_normal("vae_z_full", (1, 16, 3, 60, 104))
+    out = vae.decode(z.cuda()).sample
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (1, 3, 9, 480, 832)
+    sub, ref = out[..., 3::8, 5::8], gold["sub8"].astype(np.float32)
+    assert rel(sub, ref) < 2e-2 and psnr(sub, ref) > 35, (rel(sub, ref), psnr(sub, ref))
+    assert np.allclose(out.mean(dim=(-1, -2)).cpu().numpy(), gold["frame_mean"], atol=2e-3)
+    assert np.allclose((out.double() ** 2).mean(dim=(-1, -2)).cpu().numpy(), gold["frame_sq"], rtol=2e-2, atol=1e-4)
+
+
 def _pp_worker(rank, world, port, q_out):
     import os
     import torch.distributed as dist

@@ -67,3 +67,21 @@ if __name__ == "__main__":
     if "--encode-only" not in sys.argv:
         gen_vae()
     gen_vae_encode()
+
+
+def gen_vae_fullres():
+    """SURVEY.md §8c pin #4: the REAL AutoencoderKLWan.decode at the benchmark's latent grid — z [1,16,3,60,104] ->
+    [1,3,9,480,832] (about 100 s on 8 host threads) — kept as a strided subsample (every 8th row / column: 60 x 104 pixels per
+    frame, all 9 frames and 3 channels, fp16) plus per-frame means so that the fixture stays small (< 400 KB)."""
+    _, _, vae = import_reference()
+    m = vae.AutoencoderKLWan().eval()
+    missing, unexpected = m.load_state_dict(synth.vae_state_dict(), strict=False)
+    assert not unexpected
+    z = synth.det_normal("vae_z_full", (1, 16, 3, 60, 104))
+    with torch.no_grad():
+        out = m.decode(z).sample
+    assert tuple(out.shape) == (1, 3, 9, 480, 832)
+    res = {"sub8": out[..., 3::8, 5::8].numpy().astype(np.float16), "frame_mean": out.mean(dim=(-1, -2)).numpy(),
+           "frame_sq": (out.double() ** 2).mean(dim=(-1, -2)).numpy()}
+    np.savez_compressed(ROOT / "tests" / "golden" / "vae_fullres_sub.npz", **res)
+    print("wrote vae_fullres_sub.npz", {k: v.shape for k, v in res.items()})
