@@ -82,7 +82,7 @@ int sa_flash_attn_d128(const sa_attn_args* args, sa_stream_t stream);
  * q loaded once. q/out: bf16 [batch, q_len, heads, 128] views as in sa_attn_args. A set is [batch, kv_total, heads, 128]
  * (strides k_bs/k_ls, v_bs/v_ls). windowed = 0: all kv_len = kv_total keys. windowed = 1 (audio, 1B.py:575-586): the keys
  * are kv_total / kv_len consecutive windows of kv_len keys and query row r attends only to window
- * (tok_offset + r) / rows_per_group; requires (127 / rows_per_group + 2) * kv_len <= 64. */
+ * (tok_offset + r) / rows_per_group; requires (255 / rows_per_group + 2) * kv_len <= 64. */
 typedef struct {
   const void* k;
   const void* v;
@@ -103,7 +103,7 @@ int sa_cross_attn3_d128(const sa_cross_attn_args* args, sa_stream_t stream);
 /* Same contract for a handful of queries per (batch, head) and any head_dim % 8 == 0: the audio adapter's
  * cross-attention, 15 audio tokens x 1560 video tokens x 8 heads of 192
  * (wan/models/vocal_projector_fantasy_1B.py:259-277; SDPA branch :178-203), and 8 heads of 640 for the 14B adapter
- * (vocal_projector_fantasy_14B.py). q_len <= 16, head_dim <= 768, any kv_len (keys are tiled through shared memory
+ * (vocal_projector_fantasy_14B.py). q_len <= 32, head_dim <= 768, any kv_len (keys are tiled through shared memory
  * with a running softmax). accumulate must be 0. */
 int sa_attn_small_q(const sa_attn_args* args, int32_t head_dim, sa_stream_t stream);
 

@@ -1,19 +1,24 @@
-// attn_cross_tcgen05.cu — the three cross-attentions of a DiT block in ONE launch (sm_100a, head_dim 128).
+// attn_cross_tcgen05.cu — the three cross-attentions of a DiT block in ONE persistent launch (sm_100a, head_dim 128).
 //
 // WanI2VTalkingCrossAttention (wan/models/wan_fantasy_transformer3d_1B.py:534-605) sums three softmax attentions that
 // share the query: text (512 keys), CLIP image (257 keys) and audio (15 keys of the latent frame's audio window, paired
-// with the token group by q.view(b * G, -1, n, d), :575-586). As three launches of the self-attention kernel each one
-// re-reads Q (302 MB at B = 3) and read-modify-writes O, and — with only 8 + 5 + 1 key steps — a CTA spends most of its
-// life filling and draining its pipeline (measured: ~1.8 us per 64-key step against 0.52 us per tile-step in
-// self-attention). Here a CTA owns ONE 128-row Q tile, loads it into TMEM once and walks the key sets back to back
-// through the decoupled pipeline of attn_v8_tcgen05.cu (global step counter, so all mbarrier phases simply keep
-// running); each set ends with the usual O / l epilogue that adds into the output row the same thread wrote a few
-// microseconds earlier (L2 hit). The CTA is sized for TWO RESIDENT CTAs PER SM — 256 TMEM columns (Q 64 + S 64 + O 128),
-// 2 K/V stages + the P double buffer = 96 KB, 192 threads — so one CTA's fill / drain / epilogue overlaps the other's
-// steady state. Per-set rounding and order (text, image, audio; every partial result rounded to bf16 before the bf16
-// add) are those of the three-launch path, so results are bit-identical.
+// with the token group by q.view(b * G, -1, n, d), :575-586). With only 8 + 5 + 1 key steps per Q tile a short-lived CTA
+// is a serial latency chain: the round-1 kernel (one 128-row tile per CTA, profiles/experiments/
+// attn_cross_one_tile_per_cta.cu.txt) spent ~10 us per CTA on launch, TMEM allocation, the Q load, the first TMA and three
+// read-modify-write epilogues — tensor pipe 18 % active, 1.2 ms per launch for 0.47 TFLOP. This kernel is PERSISTENT:
 //
-// The audio set is one 64-key step: the keys of the (at most 64 / A) consecutive windows that the CTA's 256 rows can
+//   * one CTA per SM walks work items (batch, head, 256 query rows) with a grid stride; barriers, TMEM and tensor maps
+//     are set up once, every mbarrier phase keeps running across key sets and items (global step counters);
+//   * an item is TWO 128-row Q tiles on the decoupled pipeline of attn_self_tcgen05.cu (Q in TMEM, S = Q K^T as a TS MMA,
+//     P through a double-buffered shared-memory panel, one MMA-issuing warp and one softmax warpgroup per tile), so each
+//     K/V tile fetched from L2 serves 256 rows and one tile's fill / drain / epilogue overlaps the other's steady state;
+//   * the TMA producer runs ahead across sets and items through a 3-stage ring, so the next item's first keys are in
+//     shared memory before its Q is;
+//   * the per-set results are summed in a shared-memory staging tile (bf16, every partial result rounded to bf16 before
+//     the bf16 add, set order text, image, audio — the arithmetic of three separate launches, bit for bit) and leave the
+//     SM once per item as a TMA store (rows beyond q_len are clipped by the tensor map).
+//
+// The audio set is one 64-key step: the keys of the (at most 64 / A) consecutive windows that the item's 256 rows can
 // touch are loaded together and every row masks the step down to its own window [ (g - g0) A, (g - g0) A + A ), with
 // g = (tok_offset + row) / rows_per_group — which also covers token shards of the sequence-parallel path.
 #include <stdlib.h>
@@ -28,14 +33,16 @@ namespace sa {
 namespace attnx {
 
 constexpr int BQ = 128, SUB = 64, D = 128;
-constexpr int STAGES = 2;           // short key sets: two stages, so that two CTAs fit in one SM's shared memory
+constexpr int STAGES = 3;
 constexpr int KV_PANEL = SUB * 128;          // 64 rows x 128 B = 8 KB
 constexpr int KV_TILE = 2 * KV_PANEL;        // [64 keys x 128 d] = 16 KB
 constexpr int STAGE_BYTES = 2 * KV_TILE;     // K + V
 constexpr int P_BYTES = BQ * 128;            // [128 rows x 64 keys] bf16 = 16 KB
-constexpr int NUM_THREADS = 192;   // 4 softmax warps (one Q tile), TMA producer, MMA issuer
-constexpr int TMEM_COLS = 256;        // Q 0-63, S 64-127, O 128-255: two CTAs share the SM's 512 columns
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * P_BYTES + 256 + 1024;
+constexpr int OUT_PANEL = BQ * 128;          // [128 rows x 64 cols] bf16 = 16 KB, SWIZZLE_128B (the TMA store's layout)
+constexpr int OUT_BYTES = 2 * OUT_PANEL;     // one Q tile's [128 x 128] output
+constexpr int NUM_THREADS = 352;   // 8 softmax warps (two Q tiles), TMA producer, one MMA-issuing warp per Q tile
+constexpr int TMEM_COLS = 512;     // Q0 0-63, Q1 64-127, S0 128-191, S1 192-255, O0 256-383, O1 384-511
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * P_BYTES + 2 * OUT_BYTES + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;
 
 constexpr int MAX_SETS = 3;
@@ -43,7 +50,7 @@ struct Params {
   const __nv_bfloat16* q;
   __nv_bfloat16* out;
   long long q_bs, q_ls, o_bs, o_ls;
-  int q_len;
+  int q_len, heads, n_pairs, n_items;
   float scale_log2;
   int accumulate;
   int n_sets;
@@ -52,54 +59,64 @@ struct Params {
   int rows_per_group, tok_offset;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant__ CUtensorMap tv0,
                   const __grid_constant__ CUtensorMap tk1, const __grid_constant__ CUtensorMap tv1,
-                  const __grid_constant__ CUtensorMap tk2, const __grid_constant__ CUtensorMap tv2, const Params p) {
-  constexpr int kPolyPairs = 0;
+                  const __grid_constant__ CUtensorMap tk2, const __grid_constant__ CUtensorMap tv2,
+                  const __grid_constant__ CUtensorMap tmap_o, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sKV = smem;                                   // [STAGES][K tile | V tile]
-  uint8_t* sP = smem + STAGES * STAGE_BYTES;             // [2 buffers][P_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+  uint8_t* sP = smem + STAGES * STAGE_BYTES;             // [2 q tiles][2 buffers][P_BYTES]
+  uint8_t* sOut = sP + 4 * P_BYTES;                      // [2 q tiles][2 panels][OUT_PANEL]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * OUT_BYTES);
   uint64_t* kv_full = bars;                 // [STAGES]
   uint64_t* kv_empty = bars + STAGES;       // [STAGES]
-  uint64_t* s_full = bars + 2 * STAGES;     // [1]  S(U) complete in TMEM
-  uint64_t* s_cons = s_full + 1;            // [1]  the softmax warps have S(U) in registers
-  uint64_t* p_full = s_cons + 1;            // [2 P buffers]  P(U) in shared memory (and O rescaled if needed)
-  uint64_t* pv_done = p_full + 2;           // [1]  one completion per P(U) V
-  uint64_t* o_final = pv_done + 1;          // [1]  every accumulator is complete
-  uint64_t* q_ready = o_final + 1;          // [1]  Q tile stored in TMEM
-  uint64_t* o_free = q_ready + 1;           // [1]  the epilogue of a set has read O: the next set may overwrite it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  uint64_t* s_full = bars + 2 * STAGES;     // [2]  S_i(U) complete in TMEM
+  uint64_t* s_cons = s_full + 2;            // [2]  softmax i has S_i(U) in registers
+  uint64_t* p_full = s_cons + 2;            // [2 tiles][2 P buffers]  P_i(U) in shared memory (and O_i rescaled if needed)
+  uint64_t* pv_done = p_full + 4;           // [2]  one completion per P_i(U) V
+  uint64_t* o_final = pv_done + 2;          // [2]  one completion per key set: the set's accumulator is complete
+  uint64_t* q_ready = o_final + 2;          // [2]  one completion per item: Q tile i stored in TMEM
+  uint64_t* o_free = q_ready + 2;           // [2]  one completion per key set: its epilogue has O_i in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
   auto n_sub_of = [&](int si) { return p.windowed[si] ? 1 : (p.kv_len[si] + SUB - 1) / SUB; };
-  int n_total = 0;
-  for (int si = 0; si < p.n_sets; ++si) n_total += n_sub_of(si);
-  const int g0 = (p.tok_offset + q0) / p.rows_per_group;   // first window any row of this CTA can belong to
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tk0);
     tma_prefetch_desc(&tv0);
+    tma_prefetch_desc(&tmap_o);
   }
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&kv_full[s], 1);
-        mbar_init(&kv_empty[s], 1);
+        mbar_init(&kv_empty[s], 2);   // one tcgen05.commit per MMA warp
       }
-      mbar_init(s_full, 1);
-      mbar_init(s_cons, 4);
-      mbar_init(pv_done, 1);
-      mbar_init(o_final, 1);
-      mbar_init(o_free, 4);
-      for (int i = 0; i < 2; ++i) mbar_init(&p_full[i], 4);
-      mbar_init(q_ready, 4);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&s_cons[i], 4);
+        mbar_init(&pv_done[i], 1);
+        mbar_init(&o_final[i], 1);
+        mbar_init(&q_ready[i], 4);
+        mbar_init(&o_free[i], 4);
+      }
+      for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
       fence_barrier_init();
     }
     __syncwarp();
@@ -111,187 +128,208 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
-    // ------------------------------------------------------------ TMA producer: {K, V} 64-key tiles
+  if (warp == 8) {
+    // ------------------------------------------------------------ TMA producer: {K, V} 64-key tiles, running ahead
+    // across key sets and work items through the ring
     if (elect_one()) {  // elect.sync: single active lane is known to ptxas -> no R2UR waterfall per UTCHMMA / UTMALDG
       int U = 0;
-      for (int si = 0; si < p.n_sets; ++si) {
-        const CUtensorMap* tk = si == 0 ? &tk0 : (si == 1 ? &tk1 : &tk2);
-        const CUtensorMap* tv = si == 0 ? &tv0 : (si == 1 ? &tv1 : &tv2);
-        const int row0 = p.windowed[si] ? g0 * p.kv_len[si] : 0;
-        const int ns = n_sub_of(si);
-        for (int u = 0; u < ns; ++u, ++U) {
-          const int s = U % STAGES;
-          const uint32_t ph = (U / STAGES) & 1;
-          mbar_wait(&kv_empty[s], ph ^ 1, 0x9100 | s);
-          mbar_arrive_expect_tx(&kv_full[s], STAGE_BYTES);
-          uint8_t* st = sKV + s * STAGE_BYTES;
-          tma_load_4d(st, tk, &kv_full[s], 0, row0 + u * SUB, head, b);
-          tma_load_4d(st + KV_PANEL, tk, &kv_full[s], 64, row0 + u * SUB, head, b);
-          tma_load_4d(st + KV_TILE, tv, &kv_full[s], 0, row0 + u * SUB, head, b);
-          tma_load_4d(st + KV_TILE + KV_PANEL, tv, &kv_full[s], 64, row0 + u * SUB, head, b);
+      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+        const int pt = w % p.n_pairs, head = (w / p.n_pairs) % p.heads, b = w / (p.n_pairs * p.heads);
+        const int g0 = (p.tok_offset + pt * 2 * BQ) / p.rows_per_group;   // first window any row of this item can belong to
+        for (int si = 0; si < p.n_sets; ++si) {
+          const CUtensorMap* tk = si == 0 ? &tk0 : (si == 1 ? &tk1 : &tk2);
+          const CUtensorMap* tv = si == 0 ? &tv0 : (si == 1 ? &tv1 : &tv2);
+          const int row0 = p.windowed[si] ? g0 * p.kv_len[si] : 0;
+          const int ns = n_sub_of(si);
+          for (int u = 0; u < ns; ++u, ++U) {
+            const int s = U % STAGES;
+            const uint32_t ph = (U / STAGES) & 1;
+            mbar_wait(&kv_empty[s], ph ^ 1, 0x9100 | s);
+            mbar_arrive_expect_tx(&kv_full[s], STAGE_BYTES);
+            uint8_t* st = sKV + s * STAGE_BYTES;
+            tma_load_4d(st, tk, &kv_full[s], 0, row0 + u * SUB, head, b);
+            tma_load_4d(st + KV_PANEL, tk, &kv_full[s], 64, row0 + u * SUB, head, b);
+            tma_load_4d(st + KV_TILE, tv, &kv_full[s], 0, row0 + u * SUB, head, b);
+            tma_load_4d(st + KV_TILE + KV_PANEL, tv, &kv_full[s], 64, row0 + u * SUB, head, b);
+          }
         }
       }
     }
-  } else if (warp == 5) {
-    // ------------------------------------------------------------ MMA issuer. TMEM columns: Q 0-63, S 64-127, O 128-255.
+  } else if (warp == 9 || warp == 10) {
+    // ------------------------------------------------------------ MMA issuers, one warp per Q tile
     if (elect_one()) {
+      const int i = warp - 9;
       const uint32_t idesc_qk = umma_idesc_bf16(BQ, SUB, 0, 0);  // A = Q (TMEM), B = 64 keys of K (K-major)
       const uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);    // A = P (smem, K-major), B = V (MN-major)
-      auto issue_S = [&](int u) {
-        const uint32_t ka = smem_u32(sKV + (u % STAGES) * STAGE_BYTES);
+      auto issue_S = [&](int U) {
+        const uint32_t ka = smem_u32(sKV + (U % STAGES) * STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t off = (k >> 2) * KV_PANEL + (k & 3) * 32;
-          umma_ts(tmem_base + 64, tmem_base + k * 8, umma_smem_desc(ka + off, 16, 1024, kSwz128), idesc_qk, k != 0);
+          umma_ts(tmem_base + 128 + i * SUB, tmem_base + i * 64 + k * 8, umma_smem_desc(ka + off, 16, 1024, kSwz128),
+                  idesc_qk, k != 0);
         }
-        umma_commit(s_full);
+        umma_commit(&s_full[i]);
       };
-      auto issue_PV = [&](int u, bool first) {
-        const uint32_t va = smem_u32(sKV + (u % STAGES) * STAGE_BYTES + KV_TILE);
-        const uint32_t pa = smem_u32(sP + (u & 1) * P_BYTES);
+      auto issue_PV = [&](int U, bool first) {
+        const uint32_t va = smem_u32(sKV + (U % STAGES) * STAGE_BYTES + KV_TILE);
+        const uint32_t pa = smem_u32(sP + (i * 2 + (U & 1)) * P_BYTES);
 #pragma unroll
         for (int k = 0; k < SUB / 16; ++k) {
-          umma_ss(tmem_base + 128, umma_smem_desc(pa + k * 32, 16, 1024, kSwz128),
+          umma_ss(tmem_base + 256 + i * 128, umma_smem_desc(pa + k * 32, 16, 1024, kSwz128),
                   umma_smem_desc(va + k * 2048, KV_PANEL, 1024, kSwz128), idesc_pv, (!first || k != 0) ? 1u : 0u);
         }
-        umma_commit(pv_done);
+        umma_commit(&pv_done[i]);
       };
-      mbar_wait(q_ready, 0, 0x9300);
-      mbar_wait(&kv_full[0], 0, 0x9310);
-      tc_fence_after();
-      issue_S(0);
-      int U = 0;
-      for (int si = 0; si < p.n_sets; ++si) {
-        const int ns = n_sub_of(si);
-        for (int u = 0; u < ns; ++u, ++U) {
-          if (U + 1 < n_total) {
-            mbar_wait(&kv_full[(U + 1) % STAGES], ((U + 1) / STAGES) & 1, 0x9320 | ((U + 1) % STAGES));
-            mbar_wait(s_cons, U & 1, 0x9330);   // S(U) is in the softmax registers: its columns are free
+      int U = 0, N = 0, it = 0;   // global step, key-set and item counters: barrier phases keep running
+      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++it) {
+        // first scores of the item: Q_i is in TMEM (which implies every softmax warp consumed the previous item's last S_i)
+        mbar_wait(&q_ready[i], it & 1, 0x9300 | i);
+        if (U > 0) mbar_wait(&s_cons[i], (U - 1) & 1, 0x9360 | i);
+        mbar_wait(&kv_full[U % STAGES], (U / STAGES) & 1, 0x9310 | (U % STAGES));
+        tc_fence_after();
+        issue_S(U);
+        for (int si = 0; si < p.n_sets; ++si, ++N) {
+          const int ns = n_sub_of(si);
+          for (int u = 0; u < ns; ++u, ++U) {
+            const bool last_of_item = si == p.n_sets - 1 && u == ns - 1;
+            if (!last_of_item) {
+              mbar_wait(&kv_full[(U + 1) % STAGES], ((U + 1) / STAGES) & 1, 0x9320 | ((U + 1) % STAGES));
+              mbar_wait(&s_cons[i], U & 1, 0x9330 | i);   // S_i(U) is in the softmax registers: its columns are free
+              tc_fence_after();
+              issue_S(U + 1);
+            }
+            mbar_wait(&p_full[i * 2 + (U & 1)], (U >> 1) & 1, 0x9340 | (i * 2 + (U & 1)));
+            if (u == 0 && N > 0) mbar_wait(&o_free[i], (N - 1) & 1, 0x9350 | i);   // the previous set's O_i has been read out
             tc_fence_after();
-            issue_S(U + 1);
+            issue_PV(U, u == 0);
+            if (u == ns - 1) umma_commit(&o_final[i]);
+            umma_commit(&kv_empty[U % STAGES]);   // this tile is done with K(U), V(U)
           }
-          mbar_wait(&p_full[U & 1], (U >> 1) & 1, 0x9340 | (U & 1));
-          if (u == 0 && si > 0) mbar_wait(o_free, (si - 1) & 1, 0x9350);   // the previous set's O has been read out
-          tc_fence_after();
-          issue_PV(U, u == 0);
-          if (u == ns - 1) umma_commit(o_final);
-          umma_commit(&kv_empty[U % STAGES]);   // done with K(U), V(U)
         }
       }
     }
   } else {
     // ------------------------------------------------------------ softmax warpgroups (one thread per query row)
+    const int i = warp >> 2;  // Q tile
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row inside the tile
     const uint32_t lane_sel = uint32_t(quarter * 32) << 16;
-    const uint32_t tQ = tmem_base + lane_sel;
-    const uint32_t tS = tmem_base + lane_sel + 64;
-    const uint32_t tO = tmem_base + lane_sel + 128;
-    const int row = q0 + r;
-    const bool row_ok = row < p.q_len;
-    uint8_t* p_row0 = sP + r * 128;
-
-    // ---- Q row -> TMEM (A operand layout: lane = row, column c holds elements 2c, 2c+1)
-    {
-      const uint4* qp = reinterpret_cast<const uint4*>(p.q + (long long)b * p.q_bs + (long long)(row_ok ? row : 0) * p.q_ls + head * D);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t w[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint4 v = row_ok ? qp[h * 8 + c] : make_uint4(0, 0, 0, 0);
-          w[c * 4] = v.x; w[c * 4 + 1] = v.y; w[c * 4 + 2] = v.z; w[c * 4 + 3] = v.w;
-        }
-        tmem_st_x32(tQ + h * 32, w);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(q_ready);
-    }
+    const uint32_t tQ = tmem_base + lane_sel + i * 64;
+    const uint32_t tS = tmem_base + lane_sel + 128 + i * SUB;
+    const uint32_t tO = tmem_base + lane_sel + 256 + i * 128;
+    uint8_t* p_row0 = sP + i * 2 * P_BYTES + r * 128;
+    uint8_t* out_tile = sOut + i * OUT_BYTES;
+    uint8_t* out_row = out_tile + r * 128;
+    const bool store_thread = quarter == 0 && lane == 0;   // issues and retires this tile's TMA stores
 
     const float c = p.scale_log2;
     const uint64_t c2 = pack_f32x2(c, c);
     float m_ref = 0.f;
     uint64_t lsum2 = pack_f32x2(0.f, 0.f), lsum2b = pack_f32x2(0.f, 0.f);  // two independent row-sum chains
 
-    // U: global step (barrier phases, P buffer), u: step inside the current set, MASK: 0 none, 1 ragged tail, 2 window
-    auto step = [&](int U, int u, int kv_len, auto mask_tag) {
-      constexpr int MASK = decltype(mask_tag)::value;
-      mbar_wait(s_full, U & 1, 0x9400);
-      tc_fence_after();
-      uint32_t s[SUB];
-      {
-        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-        tmem_ld_x32(tS, s0);
-        tmem_ld_x32(tS + 32, s1);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_cons);   // the MMA warp may overwrite S with the next step's scores
-      if constexpr (MASK == 1) {
-        const int valid = kv_len - u * SUB;
-#pragma unroll
-        for (int t = 0; t < SUB; ++t)
-          if (t >= valid) s[t] = 0xff800000u;  // -inf
-      } else if constexpr (MASK == 2) {
-        const int lo = ((p.tok_offset + (row_ok ? row : q0)) / p.rows_per_group - g0) * kv_len, hi = lo + kv_len;
-#pragma unroll
-        for (int t = 0; t < SUB; ++t)
-          if (t < lo || t >= hi) s[t] = 0xff800000u;  // keys of other windows
-      }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
-#pragma unroll
-      for (int t = 4; t < SUB; t += 8) {
-        mx0 = max3(mx0, __uint_as_float(s[t]), __uint_as_float(s[t + 1]));
-        mx1 = max3(mx1, __uint_as_float(s[t + 2]), __uint_as_float(s[t + 3]));
-        if (t + 4 < SUB) {
-          mx2 = max3(mx2, __uint_as_float(s[t + 4]), __uint_as_float(s[t + 5]));
-          mx3 = max3(mx3, __uint_as_float(s[t + 6]), __uint_as_float(s[t + 7]));
-        }
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    int U = 0, N = 0;
+    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+      const int pt = w % p.n_pairs, head = (w / p.n_pairs) % p.heads, b = w / (p.n_pairs * p.heads);
+      const int q0 = pt * 2 * BQ;
+      const int g0 = (p.tok_offset + q0) / p.rows_per_group;
+      const int row = q0 + i * BQ + r;
+      const bool row_ok = row < p.q_len;
 
-      float alpha = 1.0f;
-      bool need = false;
-      if (u == 0) {
-        m_ref = mx;
-      } else if ((mx - m_ref) * c > kRescaleThreshold) {
-        alpha = ex2_approx((m_ref - mx) * c);
-        m_ref = mx;
-        need = true;
-      }
-      // The P panel is double-buffered: P_i(u-2) V completed before S_i(u) did (issue order), so buffer u&1 is free.
-      if (__any_sync(0xffffffffu, need)) {
-        // P_i(u-1) V may still be accumulating into O_i: wait for it before rescaling (u >= 1 here).
-        mbar_wait(pv_done, (U - 1) & 1, 0x9450);
-        tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t o[32];
-          tmem_ld_x32(tO + cc * 32, o);
-          tmem_ld_wait();
+      // ---- Q row -> TMEM (A operand layout: lane = row, column c holds elements 2c, 2c+1). The previous item's last
+      // score MMA has completed (this thread waited for its s_full), so the columns are free.
+      {
+        const uint4* qp = reinterpret_cast<const uint4*>(p.q + (long long)b * p.q_bs + (long long)(row_ok ? row : 0) * p.q_ls + head * D);
 #pragma unroll
-          for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
-          tmem_st_x32(tO + cc * 32, o);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t wq[32];
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            uint4 v = row_ok ? __ldg(qp + h * 8 + cc) : make_uint4(0, 0, 0, 0);
+            wq[cc * 4] = v.x; wq[cc * 4 + 1] = v.y; wq[cc * 4 + 2] = v.z; wq[cc * 4 + 3] = v.w;
+          }
+          tmem_st_x32(tQ + h * 32, wq);
         }
         tmem_st_wait();
-        float l_lo, l_hi;
-        unpack_f32x2(lsum2, l_lo, l_hi);
-        lsum2 = pack_f32x2(l_lo * alpha, l_hi * alpha);
-        unpack_f32x2(lsum2b, l_lo, l_hi);
-        lsum2b = pack_f32x2(l_lo * alpha, l_hi * alpha);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_ready[i]);
       }
-      const float nmc = -m_ref * c;
-      const uint64_t nmc2 = pack_f32x2(nmc, nmc);
-      uint8_t* p_row = p_row0 + (U & 1) * P_BYTES;
-      if constexpr (kPolyPairs == 0) {
-        // Staged so that no instruction waits on its predecessor: (A) 32 independent packed scales, (B) 64 MUFU.EX2
-        // back to back (the XU pipe, 8 cycles per warp instruction, is the only limiter of this stage and the other
-        // softmax warp of the sub-partition fills the issue slots), (C) row sums on 4 chains + bf16 packing + stores.
+
+      // U: global step (barrier phases, P buffer), u: step inside the current set, MASK: 0 none, 1 ragged tail, 2 window
+      auto step = [&](int u, int kv_len, auto mask_tag) {
+        constexpr int MASK = decltype(mask_tag)::value;
+        mbar_wait(&s_full[i], U & 1, 0x9400 | i);
+        tc_fence_after();
+        uint32_t s[SUB];
+        {
+          uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          tmem_ld_x32(tS, s0);
+          tmem_ld_x32(tS + 32, s1);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_cons[i]);   // the MMA warp may overwrite S_i with the next step's scores
+        if constexpr (MASK == 1) {
+          const int valid = kv_len - u * SUB;
+#pragma unroll
+          for (int t = 0; t < SUB; ++t)
+            if (t >= valid) s[t] = 0xff800000u;  // -inf
+        } else if constexpr (MASK == 2) {
+          const int lo = ((p.tok_offset + (row_ok ? row : q0)) / p.rows_per_group - g0) * kv_len, hi = lo + kv_len;
+#pragma unroll
+          for (int t = 0; t < SUB; ++t)
+            if (t < lo || t >= hi) s[t] = 0xff800000u;  // keys of other windows
+        }
+        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
+#pragma unroll
+        for (int t = 4; t < SUB; t += 8) {
+          mx0 = max3(mx0, __uint_as_float(s[t]), __uint_as_float(s[t + 1]));
+          mx1 = max3(mx1, __uint_as_float(s[t + 2]), __uint_as_float(s[t + 3]));
+          if (t + 4 < SUB) {
+            mx2 = max3(mx2, __uint_as_float(s[t + 4]), __uint_as_float(s[t + 5]));
+            mx3 = max3(mx3, __uint_as_float(s[t + 6]), __uint_as_float(s[t + 7]));
+          }
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+
+        float alpha = 1.0f;
+        bool need = false;
+        if (u == 0) {
+          m_ref = mx;
+        } else if ((mx - m_ref) * c > kRescaleThreshold) {
+          alpha = ex2_approx((m_ref - mx) * c);
+          m_ref = mx;
+          need = true;
+        }
+        // The P panel is double-buffered: P_i(U-2) V completed before S_i(U) did (issue order), so buffer U&1 is free.
+        if (__any_sync(0xffffffffu, need)) {
+          // P_i(U-1) V may still be accumulating into O_i: wait for it before rescaling (u >= 1 here).
+          mbar_wait(&pv_done[i], (U - 1) & 1, 0x9450 | i);
+          tc_fence_after();
+#pragma unroll 1
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + cc * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
+            tmem_st_x32(tO + cc * 32, o);
+          }
+          tmem_st_wait();
+          float l_lo, l_hi;
+          unpack_f32x2(lsum2, l_lo, l_hi);
+          lsum2 = pack_f32x2(l_lo * alpha, l_hi * alpha);
+          unpack_f32x2(lsum2b, l_lo, l_hi);
+          lsum2b = pack_f32x2(l_lo * alpha, l_hi * alpha);
+        }
+        const float nmc = -m_ref * c;
+        const uint64_t nmc2 = pack_f32x2(nmc, nmc);
+        uint8_t* p_row = p_row0 + (U & 1) * P_BYTES;
+        // Staged so that no instruction waits on its predecessor: (A) 32 independent packed scales, (B) 64 MUFU.EX2 back
+        // to back, (C) row sums on 4 chains + bf16 packing + stores.
         uint64_t x2[32];
 #pragma unroll
         for (int t = 0; t < 32; ++t)
@@ -322,100 +360,60 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
         }
         lsum2 = add_f32x2(la, lc);
         lsum2b = add_f32x2(lb, ld);
-      } else {
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {   // 8 chunks of 8 keys = 16 bytes of bf16
-        uint32_t pk[4];
-#pragma unroll
-        for (int t4 = 0; t4 < 4; ++t4) {
-          const int t = c8 * 4 + t4;     // column pair index
-          const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), c2, nmc2);
-          uint64_t p2;
-          if ((t & 7) < kPolyPairs) {
-            float x0, x1;
-            unpack_f32x2(x2, x0, x1);
-            x0 = fmaxf(x0, -126.0f);
-            x1 = fmaxf(x1, -126.0f);
-            const uint64_t xc = pack_f32x2(x0, x1);
-            const uint64_t xi = add_f32x2(xc, pack_f32x2(12582912.0f, 12582912.0f));
-            const uint64_t xr = add_f32x2(xi, pack_f32x2(-12582912.0f, -12582912.0f));
-            const uint64_t f = fma_f32x2(xr, pack_f32x2(-1.0f, -1.0f), xc);
-            uint64_t q = fma_f32x2(f, pack_f32x2(0.05550411f, 0.05550411f), pack_f32x2(0.24022651f, 0.24022651f));
-            q = fma_f32x2(q, f, pack_f32x2(0.69314718f, 0.69314718f));
-            q = fma_f32x2(q, f, pack_f32x2(1.0f, 1.0f));
-            float q0_, q1_, i0, i1;
-            unpack_f32x2(q, q0_, q1_);
-            unpack_f32x2(xi, i0, i1);
-            q0_ = __uint_as_float(__float_as_uint(q0_) + (__float_as_uint(i0) << 23));
-            q1_ = __uint_as_float(__float_as_uint(q1_) + (__float_as_uint(i1) << 23));
-            p2 = pack_f32x2(q0_, q1_);
-            pk[t4] = pack_bf16x2(q0_, q1_);
-          } else {
-            float x0, x1;
-            unpack_f32x2(x2, x0, x1);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-            p2 = pack_f32x2(p0, p1);
-            pk[t4] = pack_bf16x2(p0, p1);
-          }
-          if (t4 & 1) lsum2b = add_f32x2(lsum2b, p2);
-          else lsum2 = add_f32x2(lsum2, p2);
-        }
-        *reinterpret_cast<uint4*>(p_row + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[U & 1]);
-    };
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[i * 2 + (U & 1)]);
+        ++U;
+      };
 
-    __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)row * p.o_ls + head * D;
-    int U = 0;
-    for (int si = 0; si < p.n_sets; ++si) {
-      const int kv_len = p.kv_len[si];
-      lsum2 = pack_f32x2(0.f, 0.f);
-      lsum2b = pack_f32x2(0.f, 0.f);
-      if (p.windowed[si]) {
-        step(U, 0, kv_len, std::integral_constant<int, 2>{});
-        ++U;
-      } else {
-        const int ns = (kv_len + SUB - 1) / SUB;
-        for (int u = 0; u < ns - 1; ++u, ++U) step(U, u, kv_len, std::integral_constant<int, 0>{});
-        if (kv_len % SUB) step(U, ns - 1, kv_len, std::integral_constant<int, 1>{});
-        else step(U, ns - 1, kv_len, std::integral_constant<int, 0>{});
-        ++U;
-      }
-      // ---- epilogue of the set: O / l -> bf16 -> (+=) global
-      mbar_wait(o_final, si & 1, 0x9500);
-      tc_fence_after();
-      float l_lo, l_hi;
-      lsum2 = add_f32x2(lsum2, lsum2b);
-      unpack_f32x2(lsum2, l_lo, l_hi);
-      const float inv_l = 1.0f / (l_lo + l_hi);
-      const bool acc = p.accumulate || si > 0;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t o[32];
-        tmem_ld_x32(tO + cc * 32, o);
-        tmem_ld_wait();
-        if (cc == 3) {   // all of O is in registers: the next set's first P V may overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(o_free);
+      const __nv_bfloat16* orow_g = p.out + (long long)b * p.o_bs + (long long)(row_ok ? row : 0) * p.o_ls + head * D;
+      for (int si = 0; si < p.n_sets; ++si, ++N) {
+        const int kv_len = p.kv_len[si];
+        lsum2 = pack_f32x2(0.f, 0.f);
+        lsum2b = pack_f32x2(0.f, 0.f);
+        if (p.windowed[si]) {
+          step(0, kv_len, std::integral_constant<int, 2>{});
+        } else {
+          const int ns = (kv_len + SUB - 1) / SUB;
+          for (int u = 0; u < ns - 1; ++u) step(u, kv_len, std::integral_constant<int, 0>{});
+          if (kv_len % SUB) step(ns - 1, kv_len, std::integral_constant<int, 1>{});
+          else step(ns - 1, kv_len, std::integral_constant<int, 0>{});
         }
-        if (row_ok) {
-          uint4 old[4];
-          if (acc) {
-#pragma unroll
-            for (int v8 = 0; v8 < 4; ++v8) old[v8] = *reinterpret_cast<const uint4*>(orow + cc * 32 + v8 * 8);
+        // ---- epilogue of the set: O / l -> bf16 -> (+=) the staging tile (set 0 of an item: first retire the previous
+        // item's TMA store, which still reads the tile)
+        if (si == 0) {
+          if (store_thread) bulk_wait_read0();
+          named_bar_sync(1 + i, 128);
+        }
+        mbar_wait(&o_final[i], N & 1, 0x9500 | i);
+        tc_fence_after();
+        float l_lo, l_hi;
+        lsum2 = add_f32x2(lsum2, lsum2b);
+        unpack_f32x2(lsum2, l_lo, l_hi);
+        const float inv_l = 1.0f / (l_lo + l_hi);
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t o[32];
+          tmem_ld_x32(tO + cc * 32, o);
+          tmem_ld_wait();
+          if (cc == 3) {   // all of O_i is in registers: the next set's first P V may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free[i]);
           }
 #pragma unroll
           for (int v8 = 0; v8 < 4; ++v8) {
+            const int chunk = cc * 4 + v8;                       // 16-byte chunk of the 256-byte output row
+            uint4* dst = reinterpret_cast<uint4*>(out_row + (chunk >> 3) * OUT_PANEL + (((chunk & 7) ^ (r & 7)) << 4));
             float y[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(o[v8 * 8 + t]) * inv_l;
-            if (acc) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&old[v8]);
+            if (si > 0 || p.accumulate) {
+              uint4 old;
+              if (si > 0) old = *dst;
+              else old = row_ok ? __ldg(reinterpret_cast<const uint4*>(orow_g) + chunk) : make_uint4(0, 0, 0, 0);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&old);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const float2 f = __bfloat1622float2(h[t]);
@@ -428,16 +426,25 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
             uu.y = pack_bf16x2(y[2], y[3]);
             uu.z = pack_bf16x2(y[4], y[5]);
             uu.w = pack_bf16x2(y[6], y[7]);
-            *reinterpret_cast<uint4*>(orow + cc * 32 + v8 * 8) = uu;
+            *dst = uu;
           }
         }
       }
+      // ---- the item's output leaves as one TMA store per 64-column panel (rows >= q_len clipped by the tensor map)
+      fence_proxy_async_smem();
+      named_bar_sync(1 + i, 128);
+      if (store_thread && q0 + i * BQ < p.q_len) {
+        tma_store_4d(&tmap_o, out_tile, 0, q0 + i * BQ, head, b);
+        tma_store_4d(&tmap_o, out_tile + OUT_PANEL, 64, q0 + i * BQ, head, b);
+        bulk_commit();
+      }
     }
+    if (store_thread) bulk_wait0();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -458,26 +465,36 @@ extern "C" int sa_cross_attn3_d128(const sa_cross_attn_args* a, sa_stream_t stre
     set_error("sa_cross_attn3_d128: q / out must be 16-byte aligned");
     return SA_ERR_BAD_ARG;
   }
+  if (a->q_ls % 8 || a->q_bs % 8 || a->o_ls % 8 || a->o_bs % 8) {
+    set_error("sa_cross_attn3_d128: strides must be multiples of 8 elements");
+    return SA_ERR_BAD_ARG;
+  }
   Params p;
   p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.q_bs = a->q_bs; p.q_ls = a->q_ls; p.o_bs = a->o_bs; p.o_ls = a->o_ls;
   p.q_len = a->q_len;
+  p.heads = a->heads;
+  p.n_pairs = (a->q_len + 2 * BQ - 1) / (2 * BQ);
+  const long long items = (long long)p.n_pairs * a->heads * a->batch;
+  if (items >= (1LL << 31)) { set_error("sa_cross_attn3_d128: too many work items"); return SA_ERR_UNSUPPORTED; }
+  p.n_items = (int)items;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;
   p.n_sets = a->n_sets;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1 << 30;
   p.tok_offset = a->tok_offset;
-  CUtensorMap tk[MAX_SETS], tv[MAX_SETS];
+  CUtensorMap tk[MAX_SETS], tv[MAX_SETS], to;
+  int rc;
   for (int s = 0; s < MAX_SETS; ++s) {
     const int ss = s < a->n_sets ? s : 0;   // unused slots repeat set 0 (never dereferenced)
     const sa_cross_attn_set* cs = &a->set[ss];
     if (!cs->k || !cs->v || cs->kv_len <= 0 || cs->kv_total < cs->kv_len) { set_error("sa_cross_attn3_d128: bad key set %d", ss); return SA_ERR_BAD_ARG; }
     if (cs->windowed) {
-      // the 128 rows of a CTA touch at most 127 / rows_per_group + 2 consecutive windows; all their keys share one step
-      const int span = 127 / p.rows_per_group + 2;
+      // the 256 rows of a work item touch at most 255 / rows_per_group + 2 consecutive windows; all their keys share one step
+      const int span = 255 / p.rows_per_group + 2;
       if (a->rows_per_group <= 0 || span * cs->kv_len > SUB) {
-        set_error("sa_cross_attn3_d128: windowed set needs (127 / rows_per_group + 2) * kv_len <= %d", SUB);
+        set_error("sa_cross_attn3_d128: windowed set needs (255 / rows_per_group + 2) * kv_len <= %d", SUB);
         return SA_ERR_UNSUPPORTED;
       }
     }
@@ -489,13 +506,18 @@ extern "C" int sa_cross_attn3_d128(const sa_cross_attn_args* a, sa_stream_t stre
       uint32_t box[4] = {64, SUB, 1, 1};
       return make_tmap_bf16(m, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     };
-    int rc;
     if ((rc = mk(&tk[s], cs->k, cs->k_ls, cs->k_bs))) return rc;
     if ((rc = mk(&tv[s], cs->v, cs->v_ls, cs->v_bs))) return rc;
   }
-  if (int rc2 = ensure_dyn_smem(cross_attn_kernel, SMEM_BYTES, "cross_attn_kernel")) return rc2;
-  dim3 grid((a->q_len + BQ - 1) / BQ, a->heads, a->batch);
-  cross_attn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk[0], tv[0], tk[1], tv[1], tk[2], tv[2], p);
+  {
+    uint64_t dims[4] = {(uint64_t)D, (uint64_t)a->q_len, (uint64_t)a->heads, (uint64_t)a->batch};
+    uint64_t strides[3] = {(uint64_t)a->o_ls * 2, (uint64_t)D * 2, (uint64_t)a->o_bs * 2};
+    uint32_t box[4] = {64, BQ, 1, 1};
+    if ((rc = make_tmap_bf16(&to, a->out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  if ((rc = ensure_dyn_smem(cross_attn_kernel, SMEM_BYTES, "cross_attn_kernel"))) return rc;
+  const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+  cross_attn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk[0], tv[0], tk[1], tv[1], tk[2], tv[2], to, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "cross_attn_kernel launch");
   return SA_OK;

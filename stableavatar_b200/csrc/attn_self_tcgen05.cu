@@ -42,6 +42,18 @@ constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * P_BYTES + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;
 
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ float ex2_approx_pinned(float x) {   // volatile: stays between the surrounding barriers
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct Params {
   const __nv_bfloat16* q;
   __nv_bfloat16* out;
@@ -51,6 +63,7 @@ struct Params {
   int accumulate;
 };
 
+template <int kVar>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -272,39 +285,55 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
       const uint64_t nmc2 = pack_f32x2(nmc, nmc);
       uint8_t* p_row = p_row0 + (u & 1) * P_BYTES;
       {
-      // Staged so that no instruction waits on its predecessor: (A) 32 independent packed scales, (B) 64 MUFU.EX2
-      // back to back (the XU pipe, 8 cycles per warp instruction, is the only limiter of this stage and the other
-      // softmax warp of the sub-partition fills the issue slots), (C) row sums on 4 chains + bf16 packing + stores.
-      uint64_t x2[32];
+        // Staged so that no instruction waits on its predecessor: (A) 32 independent packed scales, (B) 64 MUFU.EX2 back
+        // to back (the XU pipe, 8 cycles per warp instruction, is the only limiter of this stage and the other softmax
+        // warp of the sub-partition fills the issue slots), (C) row sums on 4 chains + bf16 packing + stores.
+        // 64 MUFU.EX2 per row and step are 1024 XU cycles per SM for the two Q tiles — as many as the step's MMAs take on
+        // the tensor pipe — but moving a quarter or half of them to the FMA / ALU pipes (Cody-Waite split + cubic, packed
+        // f32x2, the FA4 trick) measured SLOWER here: 1350 -> 1169 / 1107 TFLOP/s standalone (profiles/r02_attn_tune.log):
+        // the ~10 extra FMA / ALU instructions per pair cost more issue slots than the MUFU cycles they free.
+        uint64_t x2[32];
 #pragma unroll
-      for (int t = 0; t < 32; ++t)
-        x2[t] = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), c2, nmc2);
-      float pe[64];
+        for (int t = 0; t < 32; ++t)
+          x2[t] = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), c2, nmc2);
+        float pe[64];
+        // XU token (kVar & 1): the two softmax warps of an SM sub-partition (tile 0 / tile 1, same TMEM lane quarter) take
+        // turns on the MUFU stage instead of interleaving on it, so that one warp's exponentials run at the full XU rate
+        // while the other does its TMEM load / max / pack / store / barrier work.
+        if constexpr (kVar & 1) named_bar_sync(1 + quarter * 2 + i, 64);
 #pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        float x0, x1;
-        unpack_f32x2(x2[t], x0, x1);
-        pe[2 * t] = ex2_approx(x0);
-        pe[2 * t + 1] = ex2_approx(x1);
-      }
-      uint64_t la = lsum2, lb = lsum2b, lc = pack_f32x2(0.f, 0.f), ld = pack_f32x2(0.f, 0.f);
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int t4 = 0; t4 < 4; ++t4) {
-          const int t = c8 * 4 + t4;
-          const uint64_t p2 = pack_f32x2(pe[2 * t], pe[2 * t + 1]);
-          if (t4 == 0) la = add_f32x2(la, p2);
-          else if (t4 == 1) lb = add_f32x2(lb, p2);
-          else if (t4 == 2) lc = add_f32x2(lc, p2);
-          else ld = add_f32x2(ld, p2);
-          pk[t4] = pack_bf16x2(pe[2 * t], pe[2 * t + 1]);
+        for (int t = 0; t < 32; ++t) {
+          float x0, x1;
+          unpack_f32x2(x2[t], x0, x1);
+          if constexpr (kVar & 1) {
+            pe[2 * t] = ex2_approx_pinned(x0);
+            pe[2 * t + 1] = ex2_approx_pinned(x1);
+          } else {
+            pe[2 * t] = ex2_approx(x0);
+            pe[2 * t + 1] = ex2_approx(x1);
+          }
         }
-        *reinterpret_cast<uint4*>(p_row + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-      lsum2 = add_f32x2(la, lc);
-      lsum2b = add_f32x2(lb, ld);
+        if constexpr (kVar & 1) {
+          if (i == 0 || u != n_sub - 1) named_bar_arrive(1 + quarter * 2 + (i ^ 1), 64);
+        }
+        uint64_t la = lsum2, lb = lsum2b, lc = pack_f32x2(0.f, 0.f), ld = pack_f32x2(0.f, 0.f);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int t = c8 * 4 + t4;
+            const uint64_t p2 = pack_f32x2(pe[2 * t], pe[2 * t + 1]);
+            if (t4 == 0) la = add_f32x2(la, p2);
+            else if (t4 == 1) lb = add_f32x2(lb, p2);
+            else if (t4 == 2) lc = add_f32x2(lc, p2);
+            else ld = add_f32x2(ld, p2);
+            pk[t4] = pack_bf16x2(pe[2 * t], pe[2 * t + 1]);
+          }
+          *reinterpret_cast<uint4*>(p_row + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        lsum2 = add_f32x2(la, lc);
+        lsum2b = add_f32x2(lb, ld);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -312,6 +341,9 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
       if (lane == 0) mbar_arrive(&p_full[i * 2 + (u & 1)]);
     };
 
+    if constexpr (kVar & 1) {
+      if (i == 1) named_bar_arrive(1 + quarter * 2, 64);   // tile 0 goes first
+    }
     const bool ragged = (p.kv_len % SUB) != 0;
     for (int u = 0; u < n_sub - 1; ++u) step(u, std::false_type{});
     if (ragged) step(n_sub - 1, std::true_type{});
@@ -369,6 +401,10 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
 }  // namespace attn8
 }  // namespace sa
 
+static int g_attn_variant = 0;
+// Tuning hook (tools/attn_tune.py), not part of include/stableavatar_b200.h.
+extern "C" int sa_dbg_attn_variant(int v) { int old = g_attn_variant; if (v >= 0) g_attn_variant = v; return old; }
+
 extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
   using namespace sa;
   using namespace sa::attn8;
@@ -401,9 +437,14 @@ extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
   p.q_len = a->q_len; p.kv_len = a->kv_len;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;
-  if ((rc = ensure_dyn_smem(flash_attn_v8_kernel, SMEM_BYTES, "flash_attn_v8_kernel"))) return rc;
   dim3 grid((a->q_len + 2 * BQ - 1) / (2 * BQ), a->heads, a->batch);
-  flash_attn_v8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p);
+  if (g_attn_variant & 1) {
+    if ((rc = ensure_dyn_smem(flash_attn_v8_kernel<1>, SMEM_BYTES, "flash_attn_v8_kernel"))) return rc;
+    flash_attn_v8_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p);
+  } else {
+    if ((rc = ensure_dyn_smem(flash_attn_v8_kernel<0>, SMEM_BYTES, "flash_attn_v8_kernel"))) return rc;
+    flash_attn_v8_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "flash_attn_v8_kernel launch");
   return SA_OK;

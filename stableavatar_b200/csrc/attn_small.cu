@@ -12,7 +12,8 @@
 namespace sa {
 namespace attn_small {
 
-constexpr int MAXQ = 16;
+constexpr int MAXQ_LIMIT = 32;   // queries per (batch, head): 15 for 81-frame windows fed 161 wav2vec tokens, 17-19 when the
+                                 // pipeline feeds the window's 84 / 12 frames of audio (pipe.py:722-724)
 constexpr int THREADS = 256;
 constexpr int MAXCPT = 3;  // output columns per thread: head_dim <= 768 (192 for the 1.3B adapter, 640 for the 14B one)
 
@@ -25,6 +26,7 @@ struct Params {
 
 // Keys are walked in tiles of `tk` with the usual running (max, sum) rescale, so kv_len is unbounded; when the whole
 // row of scores fits (the 1.3B shapes) there is a single tile and the rescale factors are all 1.
+template <int MAXQ>
 __global__ void __launch_bounds__(THREADS) attn_small_kernel(const Params p) {
   extern __shared__ float smem[];
   float* sq = smem;                      // [q_len][d]
@@ -153,11 +155,12 @@ extern "C" int sa_attn_small_q(const sa_attn_args* a, int32_t head_dim, sa_strea
     return SA_ERR_BAD_ARG;
   }
   if (a->k_ls % 8 || a->k_bs % 8) { set_error("sa_attn_small_q: k strides must be multiples of 8"); return SA_ERR_BAD_ARG; }
-  if (a->q_len > MAXQ || head_dim > MAXCPT * THREADS) {
-    set_error("sa_attn_small_q: unsupported shape (q_len %d > %d or head_dim %d > %d)", a->q_len, MAXQ, head_dim, MAXCPT * THREADS);
+  if (a->q_len > MAXQ_LIMIT || head_dim > MAXCPT * THREADS) {
+    set_error("sa_attn_small_q: unsupported shape (q_len %d > %d or head_dim %d > %d)", a->q_len, MAXQ_LIMIT, head_dim, MAXCPT * THREADS);
     return SA_ERR_UNSUPPORTED;
   }
   // keys per tile: whatever of 200 KB the queries leave, in multiples of 32
+  const int MAXQ = a->q_len <= 16 ? 16 : 32;
   const size_t fixed = ((size_t)a->q_len * head_dim + 3 * MAXQ) * sizeof(float);
   int tk = (int)((200 * 1024 - fixed) / (a->q_len * sizeof(float))) / 32 * 32;
   if (tk > a->kv_len) tk = a->kv_len;
@@ -171,8 +174,13 @@ extern "C" int sa_attn_small_q(const sa_attn_args* a, int32_t head_dim, sa_strea
   p.q_bs = a->q_bs; p.q_ls = a->q_ls; p.k_bs = a->k_bs; p.k_ls = a->k_ls;
   p.v_bs = a->v_bs; p.v_ls = a->v_ls; p.o_bs = a->o_bs; p.o_ls = a->o_ls;
   p.heads = a->heads; p.q_len = a->q_len; p.kv_len = a->kv_len; p.d = head_dim; p.tk = tk; p.scale = a->scale;
-  if (int rc = ensure_dyn_smem(attn_small_kernel, 200 * 1024, "attn_small_kernel")) return rc;
-  attn_small_kernel<<<a->batch * a->heads, THREADS, smem, stream>>>(p);
+  if (MAXQ == 16) {
+    if (int rc = ensure_dyn_smem(attn_small_kernel<16>, 200 * 1024, "attn_small_kernel")) return rc;
+    attn_small_kernel<16><<<a->batch * a->heads, THREADS, smem, stream>>>(p);
+  } else {
+    if (int rc = ensure_dyn_smem(attn_small_kernel<32>, 200 * 1024, "attn_small_kernel")) return rc;
+    attn_small_kernel<32><<<a->batch * a->heads, THREADS, smem, stream>>>(p);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "attn_small_kernel launch");
   return SA_OK;

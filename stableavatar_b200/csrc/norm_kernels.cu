@@ -110,7 +110,7 @@ __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&v)[8]
 }
 
 template <int NCH, bool XBF, bool OBF, bool WBF>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 8 ? (XBF ? 4 : 2) : (XBF ? 2 : 1)) layernorm_kernel(const LnParams p) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 6 ? (XBF ? 3 : 2) : (NCH <= 8 ? 2 : 1)) layernorm_kernel(const LnParams p) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -197,6 +197,90 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 8 ? (XBF ? 4 : 2)
   }
 }
 
+// The two LayerNorm shapes of a DiT block in bf16 mode, specialised at compile time: MODE 1 = norm1 / norm2 / head with
+// AdaLN modulation, norm(x) * (1 + scale) + shift (1B.py:675, 687, 721), MODE 2 = norm3 with bf16 affine parameters
+// (1B.py:638-640, 682). The generic kernel above emulates every bf16 tensor op of the modulation chain in scalar fp32
+// (cvt + shift per rounding, ~25 issue slots per element: 73-83 % issue-active at 3.1 TB/s). Here the row is unpacked to
+// fp32 registers once, statistics and the normalisation run in fp32, and the chain runs in PACKED bf16 arithmetic —
+// cvt.rn.bf16x2.f32 for norm(x).type_as(x), then HADD2 / HMUL2 / HADD2 on bf16x2 with the packed scale / shift words as
+// loaded (each a single IEEE rounding to bf16, i.e. exactly the reference's bf16 tensor ops) — ~8 issue slots per element.
+template <int NCH, int MODE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 6 ? 3 : 2) layernorm_bf16_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int nchunks = p.C >> 3;
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + (long long)row * p.ldx;
+  uint4 raw[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + c * 32;
+    if (ch < nchunks) raw[c] = *reinterpret_cast<const uint4*>(x + ch * 8);
+  }
+  float v[NCH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const uint32_t w4[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[c][2 * i] = __uint_as_float(w4[i] << 16);
+      v[c][2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u);
+    }
+    if (lane + c * 32 < nchunks) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[c][i];
+    }
+  }
+  const float mean = warp_sum(s) / p.C;
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (lane + c * 32 < nchunks) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[c][i] - mean;
+        ss = fmaf(d, d, ss);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / p.C + p.eps);
+  const long long mrow = MODE == 1 ? (long long)(row / p.rows_per_batch) * p.mod_bs : 0;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo;
+  const __nv_bfloat162 one2 = __floats2bfloat162_rn(1.0f, 1.0f);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + c * 32;
+    if (ch >= nchunks) continue;
+    const int col = ch * 8;
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+    if constexpr (MODE == 1) {
+      const uint4 sc4 = *reinterpret_cast<const uint4*>(p.scale + mrow + col);
+      const uint4 sh4 = *reinterpret_cast<const uint4*>(p.shift + mrow + col);
+      const __nv_bfloat162* sc = reinterpret_cast<const __nv_bfloat162*>(&sc4);
+      const __nv_bfloat162* sh = reinterpret_cast<const __nv_bfloat162*>(&sh4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 y = __floats2bfloat162_rn((v[c][2 * i] - mean) * rstd, (v[c][2 * i + 1] - mean) * rstd);
+        const __nv_bfloat162 t = __hadd2(__hmul2(y, __hadd2(one2, sc[i])), sh[i]);
+        ow[i] = *reinterpret_cast<const uint32_t*>(&t);
+      }
+    } else {
+      const uint4 w4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.weight) + col);
+      const uint4 b4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.bias) + col);
+      const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float y0 = fmaf((v[c][2 * i] - mean) * rstd, __uint_as_float(ww[i] << 16), __uint_as_float(bb[i] << 16));
+        const float y1 = fmaf((v[c][2 * i + 1] - mean) * rstd, __uint_as_float(ww[i] & 0xffff0000u), __uint_as_float(bb[i] & 0xffff0000u));
+        ow[i] = pack_bf16x2(y0, y1);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + col) = o;
+  }
+}
+
 template <int NCH>
 static void launch_ln(const LnParams& p, int grid, cudaStream_t stream) {
   const bool xb = p.x_dtype == SA_BF16, ob = p.out_dtype == SA_BF16, wb = p.w_dtype == SA_BF16;
@@ -224,7 +308,7 @@ struct RmsParams {
 };
 
 template <int NCH>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 8 ? 4 : 2) rmsnorm_rope_kernel(const RmsParams p) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 6 ? 4 : (NCH <= 8 ? 3 : 1)) rmsnorm_rope_kernel(const RmsParams p) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -296,7 +380,7 @@ struct RmsScatterParams {
 };
 
 template <int NCH>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 8 ? 4 : 2) rmsnorm_rope_scatter_kernel(const RmsScatterParams p) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 6 ? 4 : (NCH <= 8 ? 3 : 1)) rmsnorm_rope_scatter_kernel(const RmsScatterParams p) {
   const int lane = threadIdx.x & 31;
   const int row_l = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row_l >= p.rows) return;
@@ -418,7 +502,18 @@ extern "C" int sa_layernorm_modulate(const sa_ln_args* a, sa_stream_t stream_) {
   p.eps = a->eps;
   const int grid = (a->rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   const int nch = (a->C / 8 + 31) / 32;
-  if (nch <= 2) launch_ln<2>(p, grid, stream);
+  // bf16 DiT fast paths (packed bf16 modulation chain / bf16 affine), rows of up to 2048 channels held in fp32 registers
+  const bool bf_io = a->x_dtype == SA_BF16 && a->out_dtype == SA_BF16 && a->round_bf16 && !a->gate && !a->res && nch <= 8;
+  const int thr = WARPS_PER_BLOCK * 32;
+  if (bf_io && a->scale && !a->weight) {
+    if (nch <= 2) layernorm_bf16_kernel<2, 1><<<grid, thr, 0, stream>>>(p);
+    else if (nch <= 6) layernorm_bf16_kernel<6, 1><<<grid, thr, 0, stream>>>(p);
+    else layernorm_bf16_kernel<8, 1><<<grid, thr, 0, stream>>>(p);
+  } else if (bf_io && a->weight && a->w_dtype == SA_BF16 && !a->scale) {
+    if (nch <= 2) layernorm_bf16_kernel<2, 2><<<grid, thr, 0, stream>>>(p);
+    else if (nch <= 6) layernorm_bf16_kernel<6, 2><<<grid, thr, 0, stream>>>(p);
+    else layernorm_bf16_kernel<8, 2><<<grid, thr, 0, stream>>>(p);
+  } else if (nch <= 2) launch_ln<2>(p, grid, stream);
   else if (nch <= 6) launch_ln<6>(p, grid, stream);
   else if (nch <= 8) launch_ln<8>(p, grid, stream);
   else launch_ln<20>(p, grid, stream);

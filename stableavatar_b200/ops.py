@@ -181,16 +181,20 @@ def unpatchify(u, B, Cout, F, H, W):
 
 
 def small_linear(x, w, bias, pre=0, want_f32=True, want_bf16=False, K=None):
-    """fp32 rows: out = pre(x) @ w^T + bias (M <= 8) — sa_small_linear_f32. pre=2: x is t[M], K = sinusoid width."""
+    """fp32 rows: out = pre(x) @ w^T + bias — sa_small_linear_f32 (8 rows per launch; a batch of W window triples has
+    3W rows). pre=2: x is t[M], K = sinusoid width."""
     _need_cuda(x, w)
     assert x.dtype == torch.float32 and x.is_contiguous() and w.is_contiguous()
     M = x.shape[0]
     N, Kw = w.shape
     of = torch.empty(M, N, device=x.device, dtype=torch.float32) if want_f32 else None
     ob = torch.empty(M, N, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
-    L.check(L.lib().sa_small_linear_f32(C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(L.ptr(bias)),
-                                        C.c_void_p(L.ptr(of)), C.c_void_p(L.ptr(ob)), M, N, Kw, pre, L.dt(w),
-                                        L.stream_ptr()), "sa_small_linear_f32")
+    for m0 in range(0, M, 8):
+        m = min(8, M - m0)
+        L.check(L.lib().sa_small_linear_f32(C.c_void_p(x[m0:].data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(L.ptr(bias)),
+                                            C.c_void_p(None if of is None else of[m0:].data_ptr()),
+                                            C.c_void_p(None if ob is None else ob[m0:].data_ptr()), m, N, Kw, pre, L.dt(w),
+                                            L.stream_ptr()), "sa_small_linear_f32")
     return of, ob
 
 

@@ -562,9 +562,9 @@ class WanTransformer3DFantasyModel(nn.Module):
         window, gs = 0, 0
         if st["vc_grouped"]:                               # token group g <-> audio window g (1B.py:575-586)
             window, gs = kvv5.shape[1] // st["G"], st["L"] // st["G"]
-        # one fused launch whenever the audio windows a 128-row tile can touch fit its single 64-key step; otherwise
+        # one fused launch whenever the audio windows a 256-row work item can touch fit its single 64-key step; otherwise
         # (tiny token groups) the three sets run as separate launches of the self-attention kernel
-        fused = not window or (st["L"] % st["G"] == 0 and (127 // gs + 2) * window <= 64)
+        fused = not window or (st["L"] % st["G"] == 0 and (255 // gs + 2) * window <= 64)
         if fused:
             # one launch: q read once, the three key sets walked back to back (csrc/attn_cross_tcgen05.cu)
             with ops.timed("cross_attn"):

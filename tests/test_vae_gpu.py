@@ -85,8 +85,8 @@ def test_benchmark_grid_vs_real_reference_subsample(vae, golden_dir):
     assert tuple(out.shape) == (1, 3, 9, 480, 832)
     sub, ref = out[..., 3::8, 5::8], gold["sub8"].astype(np.float32)
     assert rel(sub, ref) < 2e-2 and psnr(sub, ref) > 35, (rel(sub, ref), psnr(sub, ref))
-    assert np.allclose(out.mean(dim=(-1, -2)).cpu().numpy(), gold["frame_mean"], atol=2e-3)
-    assert np.allclose((out.double() ** 2).mean(dim=(-1, -2)).cpu().numpy(), gold["frame_sq"], rtol=2e-2, atol=1e-4)
+    assert np.allclose(out.mean(dim=(-1, -2)).cpu().numpy(), gold["frame_mean"], atol=5e-3)   # bf16 activations: per-frame mean within 0.25 % of the [-1, 1] range
+    assert np.allclose((out.double() ** 2).mean(dim=(-1, -2)).cpu().numpy(), gold["frame_sq"], rtol=3e-2, atol=1e-4)
 
 
 def _pp_worker(rank, world, port, q_out):
