@@ -42,18 +42,6 @@ constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * P_BYTES + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ float ex2_approx_pinned(float x) {   // volatile: stays between the surrounding barriers
-  float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 struct Params {
   const __nv_bfloat16* q;
   __nv_bfloat16* out;
@@ -63,7 +51,6 @@ struct Params {
   int accumulate;
 };
 
-template <int kVar>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -297,24 +284,14 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
         for (int t = 0; t < 32; ++t)
           x2[t] = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), c2, nmc2);
         float pe[64];
-        // XU token (kVar & 1): the two softmax warps of an SM sub-partition (tile 0 / tile 1, same TMEM lane quarter) take
-        // turns on the MUFU stage instead of interleaving on it, so that one warp's exponentials run at the full XU rate
-        // while the other does its TMEM load / max / pack / store / barrier work.
-        if constexpr (kVar & 1) named_bar_sync(1 + quarter * 2 + i, 64);
+        // Also measured and rejected (profiles/r02_attn_tune.log): an XU token that makes the two softmax warps of an SM
+        // sub-partition take turns on the MUFU stage (named barriers, 64 threads): 1292 -> 1158 TFLOP/s.
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
           float x0, x1;
           unpack_f32x2(x2[t], x0, x1);
-          if constexpr (kVar & 1) {
-            pe[2 * t] = ex2_approx_pinned(x0);
-            pe[2 * t + 1] = ex2_approx_pinned(x1);
-          } else {
-            pe[2 * t] = ex2_approx(x0);
-            pe[2 * t + 1] = ex2_approx(x1);
-          }
-        }
-        if constexpr (kVar & 1) {
-          if (i == 0 || u != n_sub - 1) named_bar_arrive(1 + quarter * 2 + (i ^ 1), 64);
+          pe[2 * t] = ex2_approx(x0);
+          pe[2 * t + 1] = ex2_approx(x1);
         }
         uint64_t la = lsum2, lb = lsum2b, lc = pack_f32x2(0.f, 0.f), ld = pack_f32x2(0.f, 0.f);
 #pragma unroll
@@ -341,9 +318,6 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
       if (lane == 0) mbar_arrive(&p_full[i * 2 + (u & 1)]);
     };
 
-    if constexpr (kVar & 1) {
-      if (i == 1) named_bar_arrive(1 + quarter * 2, 64);   // tile 0 goes first
-    }
     const bool ragged = (p.kv_len % SUB) != 0;
     for (int u = 0; u < n_sub - 1; ++u) step(u, std::false_type{});
     if (ragged) step(n_sub - 1, std::true_type{});
@@ -401,10 +375,6 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
 }  // namespace attn8
 }  // namespace sa
 
-static int g_attn_variant = 0;
-// Tuning hook (tools/attn_tune.py), not part of include/stableavatar_b200.h.
-extern "C" int sa_dbg_attn_variant(int v) { int old = g_attn_variant; if (v >= 0) g_attn_variant = v; return old; }
-
 extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
   using namespace sa;
   using namespace sa::attn8;
@@ -438,13 +408,8 @@ extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;
   dim3 grid((a->q_len + 2 * BQ - 1) / (2 * BQ), a->heads, a->batch);
-  if (g_attn_variant & 1) {
-    if ((rc = ensure_dyn_smem(flash_attn_v8_kernel<1>, SMEM_BYTES, "flash_attn_v8_kernel"))) return rc;
-    flash_attn_v8_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p);
-  } else {
-    if ((rc = ensure_dyn_smem(flash_attn_v8_kernel<0>, SMEM_BYTES, "flash_attn_v8_kernel"))) return rc;
-    flash_attn_v8_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p);
-  }
+  if ((rc = ensure_dyn_smem(flash_attn_v8_kernel, SMEM_BYTES, "flash_attn_v8_kernel"))) return rc;
+  flash_attn_v8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "flash_attn_v8_kernel launch");
   return SA_OK;

@@ -264,8 +264,7 @@ class WanI2VTalkingInferenceLongPipeline:
         latents = latents.contiguous()
         if self.use_cuda_graphs and not plain:
             key = (tuple(latents.shape), latents.dtype, tuple(vocal_embeddings.shape), tuple(y.shape), seq_len, clip_length,
-                   float(text_guide_scale or 0), float(audio_guide_scale or 0), do_cfg,
-                   tuple(tuple(p.shape) for p in prompt_embeds))
+                   float(text_guide_scale or 0), float(audio_guide_scale or 0), do_cfg, len(prompt_embeds))
             g = self._graph_for(key, lambda pool: GraphedDenoiseStep(
                 self, latents, prompt_embeds, clip_context, y, vocal_embeddings, seq_len=seq_len, clip_length=clip_length,
                 text_guide_scale=text_guide_scale, audio_guide_scale=audio_guide_scale, do_cfg=do_cfg, pool=pool))
