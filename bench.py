@@ -72,6 +72,20 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def nvlink_counters(index):
+    """Sum of the NVLink data counters of one GPU in bytes (nvidia-smi nvlink -gt d), or None where unsupported."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=10).stdout
+    except Exception:
+        return None
+    import re
+    tx = [int(m) for m in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+    rx = [int(m) for m in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+    if not tx or not rx:
+        return None
+    return sum(tx) * 1024, sum(rx) * 1024
+
+
 def workload(args):
     F_lat, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
     L = F_lat * (h // 2) * (w // 2)
@@ -163,7 +177,9 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------- B200 arm
 def build_model(cfg, device):
-    from stableavatar_b200.wan_transformer3d import WanTransformer3DFantasyModel
+    from stableavatar_b200.wan_transformer3d import WanTransformer3DFantasy14BModel, WanTransformer3DFantasyModel
+    if cfg.get("variant") == "14B":
+        WanTransformer3DFantasyModel = WanTransformer3DFantasy14BModel      # noqa: N806  (train_14B architecture, config 5)
     keys = ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim", "out_dim",
             "num_heads", "num_layers")
     old = torch.get_default_dtype()
@@ -208,7 +224,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         ops.sp_set_barrier_timeout_ms(120_000)      # the ranks of a bench run enter every forward together
-    cfg = synth.DIT_1_3B
+    cfg = synth.DIT_14B if args.model == "14b" else synth.DIT_1_3B
     F_lat, h, w, L = workload(args)
     model = build_model(cfg, dev)
     sched = FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=5.0)
@@ -218,8 +234,9 @@ def run_b200(args):
     # synthetic conditioning of the pipeline's shapes, first in pinned host memory
     inp = synth.dit_inputs(cfg, frames=args.frames, height=args.height, width=args.width, text_tokens=64)
     bf = torch.bfloat16
-    host = dict(latents=inp["x"][:1].to(bf), y=inp["y"].to(bf), clip=inp["clip_fea"].to(bf), audio=inp["vocal_embeddings"].to(bf),
-                ctx=[c.to(bf) for c in inp["context"]])
+    Wn = args.windows                                    # windows of one sliding-window step batched into the forward
+    host = dict(latents=inp["x"][:1].to(bf).repeat(Wn, 1, 1, 1, 1), y=inp["y"].to(bf), clip=inp["clip_fea"].to(bf),
+                audio=inp["vocal_embeddings"].to(bf).repeat(Wn, 1, 1), ctx=[c.to(bf) for c in inp["context"]])
     host = {k: ([t.pin_memory() for t in v] if isinstance(v, list) else v.pin_memory()) for k, v in host.items()}
     h2d_bytes = sum(t.numel() * 2 for t in (host["latents"], host["y"], host["clip"], host["audio"])) + \
         sum(t.numel() * 2 for t in host["ctx"])
@@ -246,9 +263,10 @@ def run_b200(args):
     # inputs on every rank (the single-GPU semantics are the oracle of the SP path), max over ranks
     sp_parity = None
     if world > 1:
-        kw = dict(x=resident["latents"].expand(3, -1, -1, -1, -1).contiguous(), t=torch.full((3,), 900.0, device=dev),
+        from stableavatar_b200.pipeline import _frames_kwarg
+        kw = dict(x=resident["latents"][:1].expand(3, -1, -1, -1, -1).contiguous(), t=torch.full((3,), 900.0, device=dev),
                   context=resident["ctx"], seq_len=L, clip_fea=resident["clip"], y=resident["y"],
-                  vocal_embeddings=resident["audio"], video_sample_n_frames=args.frames)
+                  vocal_embeddings=resident["audio"][:3], **_frames_kwarg(model, args.frames))
         single = model(**kw).float()
         model.enable_multi_gpus_inference()
         sp_out = model(**kw).float()
@@ -278,19 +296,19 @@ def run_b200(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    nvl0 = nvlink_counters(local) if (world > 1 and rank == 0) else None
     e0.record()
     for i in range(args.steps):
         step(resident, i)
     e1.record()
     barrier()
+    nvl1 = nvlink_counters(local) if nvl0 is not None else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     clocks = sampler.summary() if sampler else None
 
     # ---- instrumented pass: the same K steps launched eagerly, with CUDA events around the dominant kernels on the
     # launching stream (events cannot be read back from inside a replayed graph) and the launch counter running.
-    # Under sequence parallelism the product path pipelines the exchange under the attention of the neighbouring CFG
-    # samples (one "sp_attn_region" per block); a second pass with the pipeline off times attention and the two
-    # exchanges on their own, so that exposed = region - attention can be reported.
+    # Under sequence parallelism a second pass times the optional per-CFG-sample exchange pipeline (model.sp_pipelined).
     def instrumented():
         ops.TIMING = {}
         L_.launch_count = 0
@@ -309,11 +327,11 @@ def run_b200(args):
     pipe.use_cuda_graphs = False
     ms_eager, tag_ms, tag_n, launches = instrumented()
     serial = None
-    if world > 1:
-        model.sp_pipelined = False
-        ms_serial, s_ms, s_n, _ = instrumented()
+    if world > 1:                 # second eager pass with the per-sample exchange pipeline (the shipped default is serial)
+        serial = dict(total=ms_eager, ms=tag_ms, n=tag_n)
         model.sp_pipelined = True
-        serial = dict(total=ms_serial, ms=s_ms, n=s_n)
+        ms_eager_pp, pp_ms, _, _ = instrumented()
+        model.sp_pipelined = False
 
     # ---- timed region 2: end to end through the pipeline API with host buffers ("e2e"): every step copies its inputs
     # from pinned host memory, runs the captured step (the conditioning changed, so the context is re-encoded) and reads
@@ -412,6 +430,7 @@ def run_b200(args):
     if rank == 0:
         peaks = load_peaks()
         total_flops, attn_flops_per_launch = step_flops(cfg, L)
+        total_flops, attn_flops_per_launch = total_flops * Wn, attn_flops_per_launch * Wn
         src = serial if serial is not None else dict(total=ms_eager, ms=tag_ms, n=tag_n)
         n_attn = src["n"].get("self_attn", 0)
         attn_avg = src["ms"].get("self_attn", 0.0) / max(1, n_attn)
@@ -419,13 +438,13 @@ def run_b200(args):
         shares = {k: v / ms_eager for k, v in tag_ms.items()}
         shares["other"] = max(0.0, 1.0 - sum(shares.values()))
         line = {
-            "metric": METRIC, "value": s_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args), "value": s_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args, L),
                        "detail": "30 blocks, CFG batch 3 + CFG/Euler, text 512 + CLIP 257 + audio 21x15; text/CLIP context encoded "
                                  "once per clip (value) / once per step (e2e: its inputs change every step)",
-                       "parallelism": f"sp{world}" if world > 1 else "single",
+                       "parallelism": f"sp{world}" if world > 1 else "single", "windows_per_step": Wn,
                        "l2_policy": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
                        "step_tflop": total_flops / 1e12,
                        "step_tflops_achieved": total_flops / s_per_step / 1e12 / world,
@@ -446,24 +465,29 @@ def run_b200(args):
                                            "and the 4x2 split at N = 8 reads each K/V chunk on two ranks)",
                          "peak_source": f"{peaks['src']} sustained bf16 (MEASURED_PEAKS.json)",
                          "launches_timed": n_attn, "avg_launch_ms": attn_avg,
-                         "timed_in": "eager pass, exchange pipeline off" if serial is not None else "eager pass"},
+                         "timed_in": "eager pass"},
             "e2e": {"value": s_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_host.numel() * 2},
             "gpu_launches": launches, "clocks": clocks,
         }
         if world > 1:
             line["sp_parity_rel_l2"] = sp_parity
             per_step = lambda d, k: d["ms"].get(k, 0.0) / args.steps  # noqa: E731
-            region = tag_ms.get("sp_attn_region", 0.0) / args.steps
+            region = pp_ms.get("sp_attn_region", 0.0) / args.steps
             attn = per_step(serial, "self_attn")
+            exposed = per_step(serial, "sp_a2a_qkv") + per_step(serial, "sp_a2a_o")
             line["sp_exchange"] = {
-                "note": "per step and rank, ms. serial_*: exchange pipeline off (scatter + barrier timed alone); region_pipelined: "
-                        "fork -> exchange || attention per CFG sample -> join + barrier, as shipped; exposed = region - attention",
-                "serial_qkv_ms": per_step(serial, "sp_a2a_qkv"), "serial_o_ms": per_step(serial, "sp_a2a_o"), "attention_ms": attn,
-                "region_pipelined_ms": region, "exposed_ms": region - attn,
-                "exposed_share_of_step": (region - attn) / (ms_eager / args.steps),
-                "eager_ms_per_step_serial": serial["total"] / args.steps}
+                "note": "per step and rank, ms, eager passes. qkv / o: scatter + flag barrier around the attention kernel (the "
+                        "shipped serial order); region_pipelined: the optional per-CFG-sample pipeline (model.sp_pipelined), "
+                        "fork -> exchange || attention per sample -> join + barrier",
+                "qkv_ms": per_step(serial, "sp_a2a_qkv"), "o_ms": per_step(serial, "sp_a2a_o"), "attention_ms": attn,
+                "exposed_ms": exposed, "exposed_share_of_step": exposed / (ms_eager / args.steps),
+                "region_pipelined_ms": region, "eager_ms_per_step_pipelined": ms_eager_pp / args.steps,
+                "nvlink_tx_bytes_per_step_gpu0": None if not (nvl0 and nvl1) else (nvl1[0] - nvl0[0]) / args.steps,
+                "nvlink_rx_bytes_per_step_gpu0": None if not (nvl0 and nvl1) else (nvl1[1] - nvl0[1]) / args.steps,
+                "nvlink_note": "nvidia-smi nvlink -gt d on GPU 0 around the timed region (driver counters, KiB granularity); "
+                               "algorithmic egress per step and rank = 30 blocks x (q + k,v to every rank of the head group + o)"}
     case = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.model == "1.3b":
         # CPU baseline: one oracle block at the full sequence length on all host threads — and the same block on the B200
         # on the same numbers: parity at the benchmarked size
         cores = host_threads()
@@ -504,7 +528,14 @@ def run_b200(args):
 
 
 def workload_name(args, L):
-    return f"1.3B audio-DiT denoise step, {args.height}x{args.width}x{args.frames}f, CFG batch 3, L={L}"
+    name = "14B (train_14B architecture)" if args.model == "14b" else "1.3B"
+    return f"{name} audio-DiT denoise step, {args.height}x{args.width}x{args.frames}f, CFG batch 3, L={L}"
+
+
+def metric_name(args):
+    if args.model == "14b":
+        return f"s/denoise-step 14B @{args.height}x{args.width}x{args.frames}f"
+    return METRIC
 
 
 def main():
@@ -513,9 +544,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="1.3b", choices=["1.3b", "14b"],
+                    help="14b: BASELINE config 5 (train_14B architecture, default 720x1280x81; VAE / clip stages skipped)")
+    ap.add_argument("--windows", type=int, default=1, help="sliding-window windows batched into one forward per step")
     ap.add_argument("--frames", type=int, default=81)
-    ap.add_argument("--height", type=int, default=480)
-    ap.add_argument("--width", type=int, default=832)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="e2e region without CUDA-graph replay")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode and measured-clip stages")
@@ -523,6 +557,12 @@ def main():
     ap.add_argument("--clip-steps", type=int, default=50, help="denoise steps of the measured clip")
     ap.add_argument("--stage-timeout", type=float, default=420.0, help="watchdog for the VAE + clip stages, seconds")
     args = ap.parse_args()
+    if args.height is None:
+        args.height = 720 if args.model == "14b" else 480
+    if args.width is None:
+        args.width = 1280 if args.model == "14b" else 832
+    if args.model == "14b":
+        args.no_vae = True
     if args.impl == "reference":
         run_reference(args)
     else:

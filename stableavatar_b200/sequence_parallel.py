@@ -361,7 +361,7 @@ def self_attention(model, qkv, sa, st):
             ops.rmsnorm_rope_(qkv[:, :C], norm[0], qkv[:, C:2 * C], norm[1], freqs=norm[2], grid=norm[3],
                               rows_per_batch=Ll, tok_offset=norm[4])
             norm = None
-        return px.attention(qkv, norm, pipelined=getattr(model, "sp_pipelined", True))
+        return px.attention(qkv, norm, pipelined=getattr(model, "sp_pipelined", False))
     ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
                       grid=st["grid"], rows_per_batch=Ll, tok_offset=st["tok0"])
     q5 = qkv.view(B, Ll, 3, nh, 128)

@@ -158,8 +158,10 @@ class WanTransformer3DFantasyModel(nn.Module):
         self.teacache = None
         self.sp_world_size, self.sp_world_rank, self.sp_group = 1, 0, None
         # sequence-parallel exchange (sequence_parallel.py): "auto" = NVLink peer stores when every rank can map its peers,
-        # else NCCL all_to_all_single; "peer" / "nccl" force one. The other two are test knobs of the peer path.
-        self.sp_exchange, self.sp_fused_norm, self.sp_pipelined = "auto", True, True
+        # else NCCL all_to_all_single; "peer" / "nccl" force one. sp_fused_norm: RMSNorm + RoPE inside the scatter kernel.
+        # sp_pipelined: exchange of CFG sample b + 1 under the attention of sample b (bit-identical; measured 2 % slower
+        # than the serial order at P = 2 because three 768-CTA attention launches fill the SMs worse than one, so off).
+        self.sp_exchange, self.sp_fused_norm, self.sp_pipelined = "auto", True, False
         self.vocal_projector = self._make_vocal_projector(dim)
         self._prep = None
         self.hooks = None          # test instrumentation: dict collecting per-block outputs when set
@@ -534,24 +536,30 @@ class WanTransformer3DFantasyModel(nn.Module):
         ch = [e[:, k * C:(k + 1) * C] for k in range(6)]                           # views, batch stride 6C
 
         # ---- self-attention (1B.py:383-413)
-        t1 = ops.layernorm(h, shift=ch[0], scale=ch[1], mod_bs=6 * C, rows_per_batch=Ll)
+        with ops.timed("norms"):
+            t1 = ops.layernorm(h, shift=ch[0], scale=ch[1], mod_bs=6 * C, rows_per_batch=Ll)
         with ops.timed("qkv_gemm"):
             qkv = ops.gemm(t1, pb["w_qkv"], pb["b_qkv"])                           # [B*Ll, 3C]
         if self.sp_world_size > 1:
             from . import sequence_parallel as sp
             a = sp.self_attention(self, qkv, sa, st)
         else:
-            ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
-                              grid=st["grid"], rows_per_batch=Ll)
+            with ops.timed("norms"):
+                ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
+                                  grid=st["grid"], rows_per_batch=Ll)
             q4 = qkv.view(B, Ll, 3, nh, 128)
             with ops.timed("self_attn"):
                 a = ops.flash_attn(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2])
-        ops.gemm(a.view(B * Ll, C), sa.o.weight, sa.o.bias, res=h, gate=ch[2], gate_ld=6 * C, rows_per_batch=Ll, out=h)
+        with ops.timed("proj_gemms"):
+            ops.gemm(a.view(B * Ll, C), sa.o.weight, sa.o.bias, res=h, gate=ch[2], gate_ld=6 * C, rows_per_batch=Ll, out=h)
 
         # ---- cross-attention: text + CLIP image + audio share q (1B.py:534-605)
-        xn = ops.layernorm(h, weight=blk.norm3.weight, bias=blk.norm3.bias)
-        q = ops.gemm(xn, ca.q.weight, ca.q.bias)
-        ops.rmsnorm_rope_(q, ca.norm_q.weight)
+        with ops.timed("norms"):
+            xn = ops.layernorm(h, weight=blk.norm3.weight, bias=blk.norm3.bias)
+        with ops.timed("proj_gemms"):
+            q = ops.gemm(xn, ca.q.weight, ca.q.bias)
+        with ops.timed("norms"):
+            ops.rmsnorm_rope_(q, ca.norm_q.weight)
         kv, kvi = st["ctx"].kv[i], st["ctx"].kvi[i]                  # text / image K (RMSNorm applied) | V, hoisted
         vc = st["vc"]
         kvv = ops.gemm(vc.view(-1, C), pb["w_kv_voc"], pb["b_kv_voc"])
@@ -578,10 +586,12 @@ class WanTransformer3DFantasyModel(nn.Module):
                     self._audio_attention(q, kvv, a, st, Ll)
                 else:
                     ops.flash_attn(q4, kvv5[:, :, 0], kvv5[:, :, 1], out=a, accumulate=True)
-        ops.gemm(a.view(B * Ll, C), ca.o.weight, ca.o.bias, res=h, out=h)
+        with ops.timed("proj_gemms"):
+            ops.gemm(a.view(B * Ll, C), ca.o.weight, ca.o.bias, res=h, out=h)
 
         # ---- FFN (1B.py:687-691)
-        t2 = ops.layernorm(h, shift=ch[3], scale=ch[4], mod_bs=6 * C, rows_per_batch=Ll)
+        with ops.timed("norms"):
+            t2 = ops.layernorm(h, shift=ch[3], scale=ch[4], mod_bs=6 * C, rows_per_batch=Ll)
         with ops.timed("ffn"):
             hid = ops.gemm(t2, blk.ffn[0].weight, blk.ffn[0].bias, act=ops.ACT_GELU_TANH)
             ops.gemm(hid, blk.ffn[2].weight, blk.ffn[2].bias, res=h, gate=ch[5], gate_ld=6 * C, rows_per_batch=Ll, out=h)

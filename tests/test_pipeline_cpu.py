@@ -229,3 +229,27 @@ def test_dsigma_falls_back_to_a_sigma_table():
         sigmas = s.sigmas
     for i in range(10):
         assert _dsigma_at(Foreign(), i) == s.dsigma_at(i)
+
+
+def test_fp8_weight_mode_gives_the_reference_values():
+    """wan/utils/fp8_optimization.py:30-45 rounds every parameter except `modulation` to float8_e4m3fn and upcasts it
+    for the forward; the B200 path keeps bf16 storage with exactly those values."""
+    from stableavatar_b200 import synth
+    from stableavatar_b200.fp8_optimization import convert_model_weight_to_float8, convert_weight_dtype_wrapper
+    from stableavatar_b200.wan_transformer3d import WanTransformer3DFantasyModel
+    cfg = dict(synth.DIT_TINY, num_layers=1)
+    keys = ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim", "out_dim",
+            "num_heads", "num_layers")
+    m = WanTransformer3DFantasyModel(**{k: cfg[k] for k in keys})
+    sd = {k: v.bfloat16() for k, v in synth.dit_state_dict(cfg).items()}
+    m.load_state_dict(sd, strict=True)
+    m = m.to(torch.bfloat16)
+    m._prep = "stale"
+    convert_model_weight_to_float8(m, exclude_module_name=["modulation", ])          # inference.py:518
+    convert_weight_dtype_wrapper(m, torch.bfloat16)
+    assert m._prep is None
+    for name, p in m.named_parameters():
+        want = sd[name] if "modulation" in name else sd[name].to(torch.float8_e4m3fn).to(torch.bfloat16)
+        assert p.dtype == torch.bfloat16 and torch.equal(p.data, want), name
+    w = m.blocks[0].ffn[0].weight
+    assert not torch.equal(w.data, sd["blocks.0.ffn.0.weight"])                      # the rounding is real

@@ -1,7 +1,7 @@
 """GPU test (-m gpu, needs >= 2 GPUs, else skipped): the sequence-parallel forward equals the single-GPU forward (the
 reference's single-GPU semantics are the oracle for SP, SURVEY.md fact #9-iii and §8c) — with the all-to-alls as direct
-NVLink peer stores pipelined per CFG sample (csrc/sp_exchange.cu, the default), as peer stores without the pipeline and
-with the norm un-fused, and over NCCL all_to_all_single (model.sp_exchange = "nccl"). Also the train_14B head count
+NVLink peer stores (csrc/sp_exchange.cu, the default), as peer stores pipelined per CFG sample, with the norm un-fused, and
+over NCCL all_to_all_single (model.sp_exchange = "nccl"). Also the train_14B head count
 (40 heads: pure Ulysses at P = 2 / 4 / 8, 20 heads per rank at P = 2)."""
 import os
 import socket
@@ -25,7 +25,8 @@ def _free_port():
     return p
 
 
-MODES = {"peer_pipelined": dict(sp_exchange="peer", sp_fused_norm=True, sp_pipelined=True),
+MODES = {"peer": dict(sp_exchange="peer"),                                      # the default: fused norm, serial order
+         "peer_pipelined": dict(sp_exchange="peer", sp_fused_norm=True, sp_pipelined=True),
          "peer_serial_unfused": dict(sp_exchange="peer", sp_fused_norm=False, sp_pipelined=False),
          "nccl": dict(sp_exchange="nccl")}
 
@@ -112,4 +113,4 @@ def test_sp_forward_equals_single_gpu(world, mode):
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sp_forward_40_heads_equals_single_gpu(world):
     """train_14B head count (wan/configs/wan_i2v_14B.py:26-35): 40 heads -> 20 / 10 / 5 heads per rank, pure Ulysses."""
-    _run(world, "peer_pipelined", "14b")
+    _run(world, "peer", "14b")
