@@ -42,6 +42,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * P_BYTES + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;
 
+constexpr int MAX_DST = 8;
 struct Params {
   const __nv_bfloat16* q;
   __nv_bfloat16* out;
@@ -49,10 +50,30 @@ struct Params {
   int q_len, kv_len;
   float scale_log2;
   int accumulate;
+  // TMA-store epilogue (accumulate == 0): query row r belongs to destination r / rows_per_dst (one tensor map each,
+  // [B, rows_per_dst, heads, 128] views). One destination = the caller's `out`; several = the sequence-parallel O exchange,
+  // where every destination is the o_recv buffer of the rank that owns those tokens (a peer mapping over NVLink).
+  int n_dst, rows_per_dst, peer_dst;
+};
+struct OutMaps {
+  CUtensorMap m[MAX_DST];
 };
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v, const Params p) {
+flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                     const __grid_constant__ OutMaps tmap_o, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sKV = smem;                                   // [STAGES][K tile | V tile]
@@ -330,21 +351,57 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
     lsum2 = add_f32x2(lsum2, lsum2b);
     unpack_f32x2(lsum2, l_lo, l_hi);
     const float inv_l = 1.0f / (l_lo + l_hi);
-    __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)row * p.o_ls + head * D;
+    if (!p.accumulate) {
+      // The tile's two P buffers are free (o_final covers the last P V): they become the staging tile — two
+      // [128 rows x 64 cols] SWIZZLE_128B panels — and the tile leaves as TMA stores: coalesced 128-byte lines instead of
+      // 16-byte fragments per thread, which is also what makes storing STRAIGHT INTO A PEER'S o_recv over NVLink efficient
+      // (the sequence-parallel O exchange then has no kernel of its own). Rows outside a destination are clipped by its
+      // tensor map, so a tile that straddles two token owners is simply stored to both.
+      uint8_t* stage = sP + i * 2 * P_BYTES;
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-      uint32_t o[32];
-      tmem_ld_x32(tO + cc * 32, o);
-      tmem_ld_wait();
-      if (row_ok) {
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t o[32];
+        tmem_ld_x32(tO + cc * 32, o);
+        tmem_ld_wait();
 #pragma unroll
         for (int v8 = 0; v8 < 4; ++v8) {
-          float y[8];
+          const int chunk = cc * 4 + v8;                       // 16-byte chunk of the 256-byte output row
+          uint4 uu;
+          uu.x = pack_bf16x2(__uint_as_float(o[v8 * 8 + 0]) * inv_l, __uint_as_float(o[v8 * 8 + 1]) * inv_l);
+          uu.y = pack_bf16x2(__uint_as_float(o[v8 * 8 + 2]) * inv_l, __uint_as_float(o[v8 * 8 + 3]) * inv_l);
+          uu.z = pack_bf16x2(__uint_as_float(o[v8 * 8 + 4]) * inv_l, __uint_as_float(o[v8 * 8 + 5]) * inv_l);
+          uu.w = pack_bf16x2(__uint_as_float(o[v8 * 8 + 6]) * inv_l, __uint_as_float(o[v8 * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(stage + (chunk >> 3) * P_BYTES + r * 128 + (((chunk & 7) ^ (r & 7)) << 4)) = uu;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + i, 128);
+      const int t0 = q0 + i * BQ;
+      if (quarter == 0 && lane == 0 && t0 < p.q_len) {
+        for (int k = t0 / p.rows_per_dst; k < p.n_dst && k * p.rows_per_dst < t0 + BQ; ++k) {
+          const int r0 = t0 - k * p.rows_per_dst;             // may be negative: rows before the destination are clipped
+          tma_store_4d(&tmap_o.m[k], stage, 0, r0, head, b);
+          tma_store_4d(&tmap_o.m[k], stage + P_BYTES, 64, r0, head, b);
+        }
+        bulk_commit();
+        if (p.peer_dst) bulk_wait0();        // peer writes are complete before the kernel (and the flag barrier after it) ends
+        else bulk_wait_read0();              // the staging tile has been read; the writes are ordered by kernel completion
+      }
+    } else {
+      __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)row * p.o_ls + head * D;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t o[32];
+        tmem_ld_x32(tO + cc * 32, o);
+        tmem_ld_wait();
+        if (row_ok) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(o[v8 * 8 + t]) * inv_l;
-          uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + v8 * 8);
-          if (p.accumulate) {
-            uint4 old = *dst;
+          for (int v8 = 0; v8 < 4; ++v8) {
+            float y[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(o[v8 * 8 + t]) * inv_l;
+            uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + v8 * 8);
+            const uint4 old = *dst;
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&old);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -352,13 +409,13 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
               y[2 * t] = f.x + bf16_round(y[2 * t]);
               y[2 * t + 1] = f.y + bf16_round(y[2 * t + 1]);
             }
+            uint4 uu;
+            uu.x = pack_bf16x2(y[0], y[1]);
+            uu.y = pack_bf16x2(y[2], y[3]);
+            uu.z = pack_bf16x2(y[4], y[5]);
+            uu.w = pack_bf16x2(y[6], y[7]);
+            *dst = uu;
           }
-          uint4 uu;
-          uu.x = pack_bf16x2(y[0], y[1]);
-          uu.y = pack_bf16x2(y[2], y[3]);
-          uu.z = pack_bf16x2(y[4], y[5]);
-          uu.w = pack_bf16x2(y[6], y[7]);
-          *dst = uu;
         }
       }
     }
@@ -375,30 +432,37 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
 }  // namespace attn8
 }  // namespace sa
 
-extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
+// dst == nullptr: ordinary call, the output goes to a->out. Otherwise the sequence-parallel O exchange: query row r is
+// stored to dst[r / rows_per_dst] at [b, r % rows_per_dst, head, :] (element strides dst_bs / dst_ls, heads 128 apart).
+static int launch_flash_attn(const sa_attn_args* a, void* const* dst, int n_dst, int rows_per_dst, long long dst_bs,
+                             long long dst_ls, cudaStream_t stream) {
   using namespace sa;
   using namespace sa::attn8;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (!a || !a->q || !a->k || !a->v || !a->out) { set_error("sa_flash_attn_d128: null pointer"); return SA_ERR_BAD_ARG; }
+  if (!a || !a->q || !a->k || !a->v || (!dst && !a->out)) { set_error("sa_flash_attn_d128: null pointer"); return SA_ERR_BAD_ARG; }
   if (a->batch <= 0 || a->heads <= 0 || a->q_len <= 0 || a->kv_len <= 0) {
     set_error("sa_flash_attn_d128: non-positive dims");
     return SA_ERR_BAD_ARG;
   }
-  if (a->q_ls % 8 || a->k_ls % 8 || a->v_ls % 8 || a->o_ls % 8 || a->q_bs % 8 || a->k_bs % 8 || a->v_bs % 8 ||
-      a->o_bs % 8) {
+  if (a->q_ls % 8 || a->k_ls % 8 || a->v_ls % 8 || a->q_bs % 8 || a->k_bs % 8 || a->v_bs % 8 ||
+      (!dst && (a->o_ls % 8 || a->o_bs % 8)) || (dst && (dst_ls % 8 || dst_bs % 8))) {
     set_error("sa_flash_attn_d128: strides must be multiples of 8 elements");
     return SA_ERR_BAD_ARG;
   }
+  if (dst && (a->accumulate || n_dst < 1 || n_dst > MAX_DST || rows_per_dst < 1 || (long long)n_dst * rows_per_dst < a->q_len)) {
+    set_error("sa_flash_attn_d128_sp: 1 <= n_dst <= %d, n_dst * rows_per_dst >= q_len, no accumulate", MAX_DST);
+    return SA_ERR_BAD_ARG;
+  }
   CUtensorMap tk, tv;
-  auto mk = [&](CUtensorMap* m, const void* base, int len, long long ls, long long bs) {
+  OutMaps to;
+  auto mk = [&](CUtensorMap* m, const void* base, int len, long long ls, long long bs, int box_rows) {
     uint64_t dims[4] = {(uint64_t)D, (uint64_t)len, (uint64_t)a->heads, (uint64_t)a->batch};
     uint64_t strides[3] = {(uint64_t)ls * 2, (uint64_t)D * 2, (uint64_t)bs * 2};
-    uint32_t box[4] = {64, SUB, 1, 1};
+    uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
     return make_tmap_bf16(m, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
   };
   int rc;
-  if ((rc = mk(&tk, a->k, a->kv_len, a->k_ls, a->k_bs))) return rc;
-  if ((rc = mk(&tv, a->v, a->kv_len, a->v_ls, a->v_bs))) return rc;
+  if ((rc = mk(&tk, a->k, a->kv_len, a->k_ls, a->k_bs, SUB))) return rc;
+  if ((rc = mk(&tv, a->v, a->kv_len, a->v_ls, a->v_bs, SUB))) return rc;
   if ((reinterpret_cast<uintptr_t>(a->q) & 15) != 0) { set_error("sa_flash_attn_d128: q must be 16-byte aligned"); return SA_ERR_BAD_ARG; }
   Params p;
   p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
@@ -407,10 +471,33 @@ extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream_) {
   p.q_len = a->q_len; p.kv_len = a->kv_len;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;
+  p.n_dst = 1; p.rows_per_dst = a->q_len; p.peer_dst = 0;
+  if (dst) {
+    p.n_dst = n_dst; p.rows_per_dst = rows_per_dst; p.peer_dst = 1;
+    for (int k = 0; k < n_dst; ++k) {
+      if (!dst[k]) { set_error("sa_flash_attn_d128_sp: null destination %d", k); return SA_ERR_BAD_ARG; }
+      if ((rc = mk(&to.m[k], dst[k], rows_per_dst, dst_ls, dst_bs, BQ))) return rc;
+    }
+    for (int k = n_dst; k < MAX_DST; ++k) to.m[k] = to.m[0];
+  } else {
+    if (!a->accumulate && (rc = mk(&to.m[0], a->out, a->q_len, a->o_ls, a->o_bs, BQ))) return rc;
+    if (a->accumulate) to.m[0] = tk;           // never dereferenced on the read-modify-write path
+    for (int k = 1; k < MAX_DST; ++k) to.m[k] = to.m[0];
+  }
   dim3 grid((a->q_len + 2 * BQ - 1) / (2 * BQ), a->heads, a->batch);
   if ((rc = ensure_dyn_smem(flash_attn_v8_kernel, SMEM_BYTES, "flash_attn_v8_kernel"))) return rc;
-  flash_attn_v8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, p);
+  flash_attn_v8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk, tv, to, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "flash_attn_v8_kernel launch");
   return SA_OK;
+}
+
+extern "C" int sa_flash_attn_d128(const sa_attn_args* a, sa_stream_t stream) {
+  return launch_flash_attn(a, nullptr, 0, 0, 0, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sa_flash_attn_d128_sp(const sa_attn_args* a, void* const* dst, int32_t n_dst, int32_t rows_per_dst,
+                                     int64_t dst_bs, int64_t dst_ls, sa_stream_t stream) {
+  if (!dst) { sa::set_error("sa_flash_attn_d128_sp: null destination table"); return sa::SA_ERR_BAD_ARG; }
+  return launch_flash_attn(a, dst, n_dst, rows_per_dst, dst_bs, dst_ls, reinterpret_cast<cudaStream_t>(stream));
 }

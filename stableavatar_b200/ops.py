@@ -85,6 +85,19 @@ def flash_attn(q, k, v, out=None, accumulate=False, scale=None):
     return out
 
 
+def flash_attn_sp(q, k, v, dst_ptrs, rows_per_dst, dst_bs, dst_ls, scale=None):
+    """flash_attn whose epilogue stores query row r straight into dst_ptrs[r // rows_per_dst] at [b, r % rows_per_dst, head]
+    (device addresses, typically peers' o_recv over NVLink) — sa_flash_attn_d128_sp, the fused sequence-parallel O exchange."""
+    _need_cuda(q, k, v)
+    if q.shape[3] != 128:
+        raise NotImplementedError("flash_attn: head_dim 128 only")
+    g = _attn_args(q, k, v, q, False, scale)                 # `out` is ignored by the entry point
+    n = len(dst_ptrs)
+    arr = (C.c_void_p * 8)(*(list(dst_ptrs) + [None] * (8 - n)))
+    L.check(L.lib().sa_flash_attn_d128_sp(C.byref(g), arr, n, rows_per_dst, C.c_int64(dst_bs), C.c_int64(dst_ls),
+                                          L.stream_ptr()), "sa_flash_attn_d128_sp")
+
+
 def attn_small_q(q, k, v, out=None, scale=None):
     """Few-queries attention (audio adapter), any head_dim % 8 == 0 — sa_attn_small_q."""
     _need_cuda(q, k, v)

@@ -211,6 +211,9 @@ class PeerExchange:
                     ptrs[j].append(self._bases[(r, handle)] + off)
         self.kv_ptrs, self.q_ptrs, self.o_ptrs, sig0 = ptrs
         self.sig_ptrs = [sig0, [q + 64 * 4 for q in sig0]]
+        # fused O exchange: the attention epilogue stores the tokens of source rank src * qs + s straight into that rank's
+        # o_recv [B, Ll, nh, d] at this rank's head columns
+        self.o_dst = [self.o_ptrs[i * pl.qs + pl.s] + pl.g * hp * d * 2 for i in range(n_src)]
         dist.barrier(group=group)                               # every rank has mapped every buffer before the first store
 
     def close(self):
@@ -252,18 +255,29 @@ class PeerExchange:
         ops.sp_scatter_o(self.o_send, self.o_ptrs, B=B, Ll=Ll, heads=nh, P=pl.world, rank=pl.rank, hg=pl.hg,
                          b_first=b_first, b_count=b_count)
 
-    def attention(self, qkv, norm, pipelined=True):
+    def _attend(self, b0, nb, fused_o):
+        """Attention of CFG samples [b0, b0 + nb) on the receive buffers, O either stored straight into the owners' o_recv
+        by the kernel's epilogue (fused_o) or into o_send for a separate scatter."""
+        B, Ll, nh, d = self.shape
+        K, V = self.kv_recv[b0:b0 + nb, :, 0], self.kv_recv[b0:b0 + nb, :, 1]
+        if fused_o:
+            off = b0 * Ll * nh * d * 2
+            ops.flash_attn_sp(self.q_recv[b0:b0 + nb], K, V, [p + off for p in self.o_dst], Ll, Ll * nh * d, nh * d)
+        else:
+            ops.flash_attn(self.q_recv[b0:b0 + nb], K, V, out=self.o_send[b0:b0 + nb])
+
+    def attention(self, qkv, norm, pipelined=False, fused_o=True):
         """Exchange + attention + exchange back for one block; returns o_recv [B, Ll, nh, d]."""
         B = self.shape[0]
-        K, V = self.kv_recv[:, :, 0], self.kv_recv[:, :, 1]
         if not pipelined or B == 1:
             with ops.timed("sp_a2a_qkv"):
                 self.scatter_qkv(qkv, norm)
                 self.barrier(0)
             with ops.timed("self_attn"):
-                ops.flash_attn(self.q_recv, K, V, out=self.o_send)
+                self._attend(0, B, fused_o)
             with ops.timed("sp_a2a_o"):
-                self.scatter_o()
+                if not fused_o:
+                    self.scatter_o()
                 self.barrier(0)
             return self.o_recv
         main = torch.cuda.current_stream(self.device)
@@ -283,8 +297,9 @@ class PeerExchange:
                 sb = self.sample_streams[b]
                 sb.wait_event(ready[b])
                 with torch.cuda.stream(sb):
-                    ops.flash_attn(self.q_recv[b:b + 1], K[b:b + 1], V[b:b + 1], out=self.o_send[b:b + 1])
-                    self.scatter_o(b, 1)
+                    self._attend(b, 1, fused_o)
+                    if not fused_o:
+                        self.scatter_o(b, 1)
                     ev = torch.cuda.Event()
                     ev.record(sb)
                 main.wait_event(ev)
@@ -361,7 +376,8 @@ def self_attention(model, qkv, sa, st):
             ops.rmsnorm_rope_(qkv[:, :C], norm[0], qkv[:, C:2 * C], norm[1], freqs=norm[2], grid=norm[3],
                               rows_per_batch=Ll, tok_offset=norm[4])
             norm = None
-        return px.attention(qkv, norm, pipelined=getattr(model, "sp_pipelined", False))
+        return px.attention(qkv, norm, pipelined=getattr(model, "sp_pipelined", False),
+                            fused_o=getattr(model, "sp_fused_o", True))
     ops.rmsnorm_rope_(qkv[:, :C], sa.norm_q.weight, qkv[:, C:2 * C], sa.norm_k.weight, freqs=st["freqs"],
                       grid=st["grid"], rows_per_batch=Ll, tok_offset=st["tok0"])
     q5 = qkv.view(B, Ll, 3, nh, 128)

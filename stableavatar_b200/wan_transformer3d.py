@@ -161,7 +161,8 @@ class WanTransformer3DFantasyModel(nn.Module):
         # else NCCL all_to_all_single; "peer" / "nccl" force one. sp_fused_norm: RMSNorm + RoPE inside the scatter kernel.
         # sp_pipelined: exchange of CFG sample b + 1 under the attention of sample b (bit-identical; measured 2 % slower
         # than the serial order at P = 2 because three 768-CTA attention launches fill the SMs worse than one, so off).
-        self.sp_exchange, self.sp_fused_norm, self.sp_pipelined = "auto", True, False
+        # sp_fused_o: the attention epilogue TMA-stores O straight into the token owners' buffers (no scatter kernel).
+        self.sp_exchange, self.sp_fused_norm, self.sp_pipelined, self.sp_fused_o = "auto", True, False, True
         self.vocal_projector = self._make_vocal_projector(dim)
         self._prep = None
         self.hooks = None          # test instrumentation: dict collecting per-block outputs when set

@@ -27,7 +27,7 @@ def _free_port():
 
 MODES = {"peer": dict(sp_exchange="peer"),                                      # the default: fused norm, serial order
          "peer_pipelined": dict(sp_exchange="peer", sp_fused_norm=True, sp_pipelined=True),
-         "peer_serial_unfused": dict(sp_exchange="peer", sp_fused_norm=False, sp_pipelined=False),
+         "peer_serial_unfused": dict(sp_exchange="peer", sp_fused_norm=False, sp_pipelined=False, sp_fused_o=False),
          "nccl": dict(sp_exchange="nccl")}
 
 

@@ -78,12 +78,20 @@ px.barrier(0)
 torch.cuda.synchronize()
 check("peer O scatter vs NCCL", torch.equal(px.o_recv, On))
 dist.barrier()
-a = px.attention(qkv, norm, pipelined=False).clone()
+a = px.attention(qkv, norm, pipelined=False, fused_o=False).clone()
 torch.cuda.synchronize()
 dist.barrier()
-b_ = px.attention(qkv, norm, pipelined=True).clone()
+b_ = px.attention(qkv, norm, pipelined=True, fused_o=False).clone()
 torch.cuda.synchronize()
 check("attention region pipelined vs serial", torch.equal(a, b_))
+dist.barrier()
+c_ = px.attention(qkv, norm, pipelined=False, fused_o=True).clone()
+torch.cuda.synchronize()
+check("attention region with O stored to the owners by the attention epilogue (TMA) vs scatter kernel", torch.equal(a, c_))
+dist.barrier()
+d_ = px.attention(qkv, norm, pipelined=True, fused_o=True).clone()
+torch.cuda.synchronize()
+check("same, pipelined per sample", torch.equal(a, d_))
 
 
 def timeit(fn, iters=10):
@@ -121,10 +129,11 @@ t_n = timeit(lambda: sp.exchange_out(pl, O, B, Ll, nh, d, None).contiguous())
 t_p = timeit(peer_o)
 log(f"O exchange: nccl (all_to_all + unpack) {t_n:.3f} ms, peer {t_p:.3f} ms")
 t_attn = timeit(lambda: ops.flash_attn(px.q_recv, px.kv_recv[:, :, 0], px.kv_recv[:, :, 1], out=px.o_send))
-t_s = timeit(lambda: px.attention(qkv, norm, pipelined=False))
-t_pp = timeit(lambda: px.attention(qkv, norm, pipelined=True))
-log(f"attention alone {t_attn:.3f} ms; region serial {t_s:.3f} ms (exposed {t_s - t_attn:.3f}); region pipelined per CFG sample "
-    f"{t_pp:.3f} ms (exposed {t_pp - t_attn:.3f})")
+t_s0 = timeit(lambda: px.attention(qkv, norm, pipelined=False, fused_o=False))
+t_s = timeit(lambda: px.attention(qkv, norm, pipelined=False, fused_o=True))
+t_pp = timeit(lambda: px.attention(qkv, norm, pipelined=True, fused_o=True))
+log(f"attention alone {t_attn:.3f} ms; region serial with scatter_o kernel {t_s0:.3f} ms (exposed {t_s0 - t_attn:.3f}); serial with "
+    f"fused O store {t_s:.3f} ms (exposed {t_s - t_attn:.3f}); pipelined per CFG sample + fused O {t_pp:.3f} ms (exposed {t_pp - t_attn:.3f})")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok_all else 1)
