@@ -71,6 +71,27 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// tcgen05.mma with the shared-memory descriptors given as {low, high} words (the high word is a compile-time constant)
+__device__ __forceinline__ void umma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 ad, {%1, %2};\n\tmov.b64 bd, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                      const __grid_constant__ OutMaps tmap_o, const Params p) {
@@ -128,6 +149,8 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Register budget: the three single-thread roles give theirs to the softmax warpgroups (two score tiles in flight).
+  // (setmaxnreg sits inside each role branch: ptxas allocates every region after a join for the smallest budget.)
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer: {K, V} 64-key tiles
     if (elect_one()) {  // elect.sync: single active lane is known to ptxas -> no R2UR waterfall per UTCHMMA / UTMALDG
@@ -149,44 +172,53 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
     // other tile is doing (a single issuer serving both tiles in a fixed order parks on the other tile's P).
     if (elect_one()) {
       const int i = warp - 9;
-      const uint32_t idesc_qk = umma_idesc_bf16(BQ, SUB, 0, 0);  // A = Q (TMEM), B = 64 keys of K (K-major)
-      const uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);    // A = P (smem, K-major), B = V (MN-major)
-      auto issue_S = [&](int u) {
-        const uint32_t ka = smem_u32(sKV + (u % STAGES) * STAGE_BYTES);
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, SUB, 0, 0);  // A = Q (TMEM), B = 64 keys of K (K-major)
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);    // A = P (smem, K-major), B = V (MN-major)
+      // This thread's serial path sits between "P_i(u) is ready" and "S_i(u+2) is issued": everything that does not depend
+      // on a barrier is prepared before the wait. Shared-memory descriptors are kept as a 32-bit low word (address >> 4 |
+      // LBO) that advances by constants and one constant high word (SBO 1024, version 1, SWIZZLE_128B).
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (kSwz128 << 29);
+      const uint32_t k_lo0 = ((smem_u32(sKV) & 0x3ffff) >> 4) | (1u << 16);                                    // LBO 16
+      const uint32_t v_lo0 = ((smem_u32(sKV + KV_TILE) & 0x3ffff) >> 4) | (uint32_t(KV_PANEL >> 4) << 16);     // LBO = panel
+      const uint32_t p_lo0 = ((smem_u32(sP + i * 2 * P_BYTES) & 0x3ffff) >> 4) | (1u << 16);
+      const uint32_t tS = tmem_base + 128 + i * SUB, tQ = tmem_base + i * 64, tO = tmem_base + 256 + i * 128;
+      auto issue_S = [&](uint32_t k_lo) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 2) * KV_PANEL + (k & 3) * 32;
-          umma_ts(tmem_base + 128 + i * SUB, tmem_base + i * 64 + k * 8, umma_smem_desc(ka + off, 16, 1024, kSwz128),
-                  idesc_qk, k != 0);
-        }
+        for (int k = 0; k < D / 16; ++k)
+          umma_ts_lh(tS, tQ + k * 8, k_lo + (k >> 2) * (KV_PANEL >> 4) + (k & 3) * 2, DESC_HI, idesc_qk, k != 0);
         umma_commit(&s_full[i]);
       };
-      auto issue_PV = [&](int u) {
-        const uint32_t va = smem_u32(sKV + (u % STAGES) * STAGE_BYTES + KV_TILE);
-        const uint32_t pa = smem_u32(sP + (i * 2 + (u & 1)) * P_BYTES);
+      auto issue_PV = [&](uint32_t p_lo, uint32_t v_lo, uint32_t acc0) {
 #pragma unroll
-        for (int k = 0; k < SUB / 16; ++k) {
-          umma_ss(tmem_base + 256 + i * 128, umma_smem_desc(pa + k * 32, 16, 1024, kSwz128),
-                  umma_smem_desc(va + k * 2048, KV_PANEL, 1024, kSwz128), idesc_pv, (u > 0 || k != 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < SUB / 16; ++k)
+          umma_ss_lh(tO, p_lo + k * 2, DESC_HI, v_lo + k * (2048 >> 4), DESC_HI, idesc_pv, k == 0 ? acc0 : 1u);
         umma_commit(&pv_done[i]);
       };
       mbar_wait(q_ready, 0, 0x8300);
       mbar_wait(&kv_full[0], 0, 0x8310);
       tc_fence_after();
-      issue_S(0);
+      issue_S(k_lo0);
+      int ws = 1, wph = 0;          // ring stage / phase of the next score tile to issue
+      auto ahead = [&](int w) {   // issue S_i(w) once K(w) has landed and S_i(w - 1) is in the softmax registers
+        uint32_t k_lo = k_lo0 + ws * (STAGE_BYTES >> 4);
+        asm volatile("" : "+r"(k_lo));
+        mbar_wait(&kv_full[ws], wph, 0x8320 | ws);
+        mbar_wait(&s_cons[i], (w - 1) & 1, 0x8330 | i);
+        tc_fence_after();
+        issue_S(k_lo);
+        if (++ws == STAGES) { ws = 0; wph ^= 1; }
+      };
+      int us = 0;
       for (int u = 0; u < n_sub; ++u) {
-        if (u + 1 < n_sub) {
-          mbar_wait(&kv_full[(u + 1) % STAGES], ((u + 1) / STAGES) & 1, 0x8320 | ((u + 1) % STAGES));
-          mbar_wait(&s_cons[i], u & 1, 0x8330 | i);   // S_i(u) is in the softmax registers: its columns are free
-          tc_fence_after();
-          issue_S(u + 1);
-        }
+        if (u + 1 < n_sub) ahead(u + 1);
+        uint32_t p_lo = p_lo0 + (u & 1) * (P_BYTES >> 4), v_lo = v_lo0 + us * (STAGE_BYTES >> 4);
+        asm volatile("" : "+r"(p_lo), "+r"(v_lo));
         mbar_wait(&p_full[i * 2 + (u & 1)], (u >> 1) & 1, 0x8340 | (i * 2 + (u & 1)));
         tc_fence_after();
-        issue_PV(u);
+        issue_PV(p_lo, v_lo, u > 0 ? 1u : 0u);
         if (u == n_sub - 1) umma_commit(&o_final[i]);
-        umma_commit(&kv_empty[u % STAGES]);   // this tile is done with K(u), V(u)
+        umma_commit(&kv_empty[us]);   // this tile is done with K(u), V(u)
+        if (++us == STAGES) us = 0;
       }
     }
   } else {
@@ -293,20 +325,21 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
       const uint64_t nmc2 = pack_f32x2(nmc, nmc);
       uint8_t* p_row = p_row0 + (u & 1) * P_BYTES;
       {
-        // Staged so that no instruction waits on its predecessor: (A) 32 independent packed scales, (B) 64 MUFU.EX2 back
-        // to back (the XU pipe, 8 cycles per warp instruction, is the only limiter of this stage and the other softmax
-        // warp of the sub-partition fills the issue slots), (C) row sums on 4 chains + bf16 packing + stores.
-        // 64 MUFU.EX2 per row and step are 1024 XU cycles per SM for the two Q tiles — as many as the step's MMAs take on
-        // the tensor pipe — but moving a quarter or half of them to the FMA / ALU pipes (Cody-Waite split + cubic, packed
-        // f32x2, the FA4 trick) measured SLOWER here: 1350 -> 1169 / 1107 TFLOP/s standalone (profiles/r02_attn_tune.log):
-        // the ~10 extra FMA / ALU instructions per pair cost more issue slots than the MUFU cycles they free.
+        // (A) 32 packed scales, (B) 64 MUFU.EX2, (C) row sums on 4 chains + bf16 packing + stores. ptxas turns (B) + (C)
+        // into a steady "MUFU, MUFU, FADD2, F2FP" stream whose stall counts (8 + 1 + 1 + 6) make one warp alone issue
+        // exactly at the XU rate (8 cycles per warp instruction); the two softmax warps of an SM sub-partition share that
+        // pipe, so a step costs each of them >= 1024 cycles of MUFU time — as much as the step's MMAs take on the tensor
+        // pipe — plus ~400 cycles of barrier waits, TMEM load, row max and fences (in-kernel event trace,
+        // profiles/r02_attn_investigation.md). Round-2 variants that attacked this and did NOT pay, all measured in one
+        // process in randomised order against this body: exponentials partly on the FMA pipes (Cody-Waite + cubic, 6-25 %
+        // of them): +-3 %, inside the clock / power noise of a power-capped part; TMEM load + row max of S(u+1) hidden under
+        // the exponentials of step u (224 registers through setmaxnreg): -8 ... -17 %; a shared 128-column score buffer
+        // with 128-key steps handed between the two Q tiles: +-2 %. Sources: profiles/experiments/.
         uint64_t x2[32];
 #pragma unroll
         for (int t = 0; t < 32; ++t)
           x2[t] = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), c2, nmc2);
         float pe[64];
-        // Also measured and rejected (profiles/r02_attn_tune.log): an XU token that makes the two softmax warps of an SM
-        // sub-partition take turns on the MUFU stage (named barriers, 64 threads): 1292 -> 1158 TFLOP/s.
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
           float x0, x1;
@@ -328,7 +361,7 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
             else ld = add_f32x2(ld, p2);
             pk[t4] = pack_bf16x2(pe[2 * t], pe[2 * t + 1]);
           }
-          *reinterpret_cast<uint4*>(p_row + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          sts128(smem_u32(p_row) + ((c8 ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
         lsum2 = add_f32x2(la, lc);
         lsum2b = add_f32x2(lb, ld);
@@ -343,6 +376,7 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
     for (int u = 0; u < n_sub - 1; ++u) step(u, std::false_type{});
     if (ragged) step(n_sub - 1, std::true_type{});
     else step(n_sub - 1, std::false_type{});
+  
 
     // ---- epilogue: O_i / l -> bf16 -> global
     mbar_wait(&o_final[i], 0, 0x4500 | i);

@@ -81,7 +81,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef SA_MBAR_TRAP_ONLY
+    // A kernel that re-partitions registers with setmaxnreg cannot contain an ABI call (ptxas then allocates the whole
+    // function for the smallest budget and spills): it gives up the diagnostic line, not the bound.
+    if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > SA_WAIT_TIMEOUT_NS) __trap();
+#else
     if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > SA_WAIT_TIMEOUT_NS) mbar_fault(tag);
+#endif
   }
 }
 

@@ -6,10 +6,12 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, ".")
-from stableavatar_b200 import ops  # noqa: E402
+from stableavatar_b200 import _lib, ops  # noqa: E402
 
 torch.manual_seed(0)
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 32760
+# development builds export sa_dev_attn_variant (A/B of kernel variants in one process); the shipped library has one kernel
+VARIANTS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [None]
 
 
 def timeit(fn, iters=8):
@@ -31,7 +33,14 @@ for B in (1, 3):
     ref = F.scaled_dot_product_attention(q[:, :2048].transpose(1, 2).float(), k.transpose(1, 2).float(), v.transpose(1, 2).float()).transpose(1, 2)
     t = timeit(lambda: F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)))
     print(f"B={B} torch SDPA: {t:.3f} ms = {flops / t / 1e9:.0f} TFLOP/s", flush=True)
-    o = ops.flash_attn(q, k, v)
-    err = ((o[:, :2048].float() - ref).norm() / ref.norm()).item()
-    t = timeit(lambda: ops.flash_attn(q, k, v))
-    print(f"B={B} flash_attn_v8: {t:.3f} ms = {flops / t / 1e9:.0f} TFLOP/s, rel-L2 vs fp32 SDPA (2048 rows) {err:.2e}", flush=True)
+    base = None
+    for var in VARIANTS:
+        if var is not None:
+            _lib.lib().sa_dev_attn_variant(var)
+        o = ops.flash_attn(q, k, v)
+        torch.cuda.synchronize()
+        err = ((o[:, :2048].float() - ref).norm() / ref.norm()).item()
+        same = "" if base is None else f", bit-equal to first variant: {torch.equal(o, base)}"
+        base = o if base is None else base
+        t = timeit(lambda: ops.flash_attn(q, k, v))
+        print(f"B={B} flash_attn variant {var}: {t:.3f} ms = {flops / t / 1e9:.0f} TFLOP/s, rel-L2 vs fp32 SDPA (2048 rows) {err:.2e}{same}", flush=True)
