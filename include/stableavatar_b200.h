@@ -80,7 +80,8 @@ int sa_flash_attn_d128(const sa_attn_args* args, sa_stream_t stream);
  * wan/dist/wan_xfuser.py:102-110): args->out is ignored; query row r is stored to dst[r / rows_per_dst] at
  * [b, r % rows_per_dst, head, :] (element strides dst_bs / dst_ls, heads 128 elements apart), each destination typically
  * the o_recv buffer of the rank that owns those tokens, mapped over NVLink (sa_ipc_open) and already offset to this rank's
- * head columns. The tile leaves as TMA stores from a shared-memory staging tile; rows outside a destination are clipped.
+ * head columns. A 128-row tile leaves as TMA stores from a shared-memory staging tile; a tile that straddles two destinations
+ * is written row by row (16-byte stores) instead.
  * 1 <= n_dst <= 8, n_dst * rows_per_dst >= q_len, accumulate must be 0. */
 int sa_flash_attn_d128_sp(const sa_attn_args* args, void* const* dst, int32_t n_dst, int32_t rows_per_dst, int64_t dst_bs,
                           int64_t dst_ls, sa_stream_t stream);

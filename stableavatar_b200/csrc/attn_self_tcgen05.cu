@@ -41,12 +41,12 @@ constexpr int NUM_THREADS = 352;   // 8 softmax warps, TMA producer, one MMA-iss
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * P_BYTES + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;
-
 constexpr int MAX_DST = 8;
+
 struct Params {
   const __nv_bfloat16* q;
-  __nv_bfloat16* out;
-  long long q_bs, q_ls, o_bs, o_ls;
+  __nv_bfloat16* dst_ptr[MAX_DST];   // destination k holds query rows [k * rows_per_dst, (k + 1) * rows_per_dst)
+  long long q_bs, q_ls, dst_bs, dst_ls;
   int q_len, kv_len;
   float scale_log2;
   int accumulate;
@@ -385,12 +385,16 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
     lsum2 = add_f32x2(lsum2, lsum2b);
     unpack_f32x2(lsum2, l_lo, l_hi);
     const float inv_l = 1.0f / (l_lo + l_hi);
-    if (!p.accumulate) {
+    const int t0 = q0 + i * BQ;
+    const int k0 = t0 / p.rows_per_dst;                        // destination of the tile's first row
+    const bool straddle = k0 + 1 < p.n_dst && (k0 + 1) * p.rows_per_dst < t0 + BQ;
+    if (!p.accumulate && !straddle) {
       // The tile's two P buffers are free (o_final covers the last P V): they become the staging tile — two
       // [128 rows x 64 cols] SWIZZLE_128B panels — and the tile leaves as TMA stores: coalesced 128-byte lines instead of
       // 16-byte fragments per thread, which is also what makes storing STRAIGHT INTO A PEER'S o_recv over NVLink efficient
-      // (the sequence-parallel O exchange then has no kernel of its own). Rows outside a destination are clipped by its
-      // tensor map, so a tile that straddles two token owners is simply stored to both.
+      // (the sequence-parallel O exchange then has no kernel of its own). A tile that straddles two token owners takes the
+      // per-row path below instead: a TMA store may run past the END of a tensor but must not start at a negative row
+      // (cudaErrorIllegalInstruction on sm_100a, found on the first 2-GPU run), and a box cannot be shortened per launch.
       uint8_t* stage = sP + i * 2 * P_BYTES;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
@@ -410,19 +414,19 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
       }
       fence_proxy_async_smem();
       named_bar_sync(1 + i, 128);
-      const int t0 = q0 + i * BQ;
       if (quarter == 0 && lane == 0 && t0 < p.q_len) {
-        for (int k = t0 / p.rows_per_dst; k < p.n_dst && k * p.rows_per_dst < t0 + BQ; ++k) {
-          const int r0 = t0 - k * p.rows_per_dst;             // may be negative: rows before the destination are clipped
-          tma_store_4d(&tmap_o.m[k], stage, 0, r0, head, b);
-          tma_store_4d(&tmap_o.m[k], stage + P_BYTES, 64, r0, head, b);
-        }
+        const int r0 = t0 - k0 * p.rows_per_dst;               // rows past the end of the destination are clipped
+        tma_store_4d(&tmap_o.m[k0], stage, 0, r0, head, b);
+        tma_store_4d(&tmap_o.m[k0], stage + P_BYTES, 64, r0, head, b);
         bulk_commit();
         if (p.peer_dst) bulk_wait0();        // peer writes are complete before the kernel (and the flag barrier after it) ends
         else bulk_wait_read0();              // the staging tile has been read; the writes are ordered by kernel completion
       }
     } else {
-      __nv_bfloat16* orow = p.out + (long long)b * p.o_bs + (long long)row * p.o_ls + head * D;
+      // one row per thread, 16-byte stores: the read-modify-write (accumulate) form, and tiles that straddle two destinations
+      const int kr = row_ok ? row / p.rows_per_dst : 0;
+      __nv_bfloat16* orow = p.dst_ptr[kr] + (long long)b * p.dst_bs + (long long)(row - kr * p.rows_per_dst) * p.dst_ls + head * D;
+      const bool rmw = p.accumulate != 0;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t o[32];
@@ -435,13 +439,15 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
 #pragma unroll
             for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(o[v8 * 8 + t]) * inv_l;
             uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + v8 * 8);
-            const uint4 old = *dst;
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&old);
+            if (rmw) {
+              const uint4 old = *dst;
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&old);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              float2 f = __bfloat1622float2(h[t]);
-              y[2 * t] = f.x + bf16_round(y[2 * t]);
-              y[2 * t + 1] = f.y + bf16_round(y[2 * t + 1]);
+              for (int t = 0; t < 4; ++t) {
+                float2 f = __bfloat1622float2(h[t]);
+                y[2 * t] = f.x + bf16_round(y[2 * t]);
+                y[2 * t + 1] = f.y + bf16_round(y[2 * t + 1]);
+              }
             }
             uint4 uu;
             uu.x = pack_bf16x2(y[0], y[1]);
@@ -500,8 +506,9 @@ static int launch_flash_attn(const sa_attn_args* a, void* const* dst, int n_dst,
   if ((reinterpret_cast<uintptr_t>(a->q) & 15) != 0) { set_error("sa_flash_attn_d128: q must be 16-byte aligned"); return SA_ERR_BAD_ARG; }
   Params p;
   p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
-  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
-  p.q_bs = a->q_bs; p.q_ls = a->q_ls; p.o_bs = a->o_bs; p.o_ls = a->o_ls;
+  for (int k = 0; k < MAX_DST; ++k) p.dst_ptr[k] = reinterpret_cast<__nv_bfloat16*>(dst ? dst[k < n_dst ? k : 0] : a->out);
+  p.q_bs = a->q_bs; p.q_ls = a->q_ls;
+  p.dst_bs = dst ? dst_bs : a->o_bs; p.dst_ls = dst ? dst_ls : a->o_ls;
   p.q_len = a->q_len; p.kv_len = a->kv_len;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;

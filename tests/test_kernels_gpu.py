@@ -47,6 +47,25 @@ def test_flash_attention_strided_qkv_views(ops):
     assert rel(out, sdpa(v5[:, :, 0], v5[:, :, 1], v5[:, :, 2])) < 5e-3
 
 
+@pytest.mark.parametrize("B,Lq,heads,n_dst,all_heads", [(2, 300, 3, 2, 5), (1, 1000, 2, 4, 2), (3, 130, 2, 1, 4), (1, 640, 1, 5, 3)])
+def test_flash_attention_row_partitioned_destinations(ops, B, Lq, heads, n_dst, all_heads):
+    """sa_flash_attn_d128_sp (the sequence-parallel O exchange fused into the epilogue) with local destinations: query row r
+    lands in dst[r // rows] at [b, r % rows, head_offset + head], bit-identical to the ordinary call; tiles that straddle two
+    destinations (negative TMA start row) and ragged last destinations included; untouched head columns stay untouched."""
+    g = torch.Generator(device="cuda").manual_seed(Lq + n_dst)
+    q, k, v = (torch.randn(B, n, heads, 128, device="cuda", generator=g).bfloat16() for n in (Lq, 333, 333))
+    want = ops.flash_attn(q, k, v)
+    rows = -(-Lq // n_dst)
+    h0 = all_heads - heads                         # this "rank" owns the last `heads` head columns of every destination
+    dst = [torch.full((B, rows, all_heads, 128), 7.0, device="cuda").bfloat16() for _ in range(n_dst)]
+    ops.flash_attn_sp(q, k, v, [d.data_ptr() + h0 * 128 * 2 for d in dst], rows, rows * all_heads * 128, all_heads * 128)
+    torch.cuda.synchronize()
+    for j, d in enumerate(dst):
+        n = min(rows, Lq - j * rows)
+        assert torch.equal(d[:, :n, h0:], want[:, j * rows:j * rows + n])
+        assert (d[:, :, :h0] == 7.0).all() and (d[:, n:, h0:] == 7.0).all()
+
+
 def test_flash_attention_large_logits_rescale_path(ops):
     """Scores that grow by far more than 2^8 along the key axis force the lazy O / l rescale."""
     g = torch.Generator(device="cuda").manual_seed(5)
