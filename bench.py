@@ -295,8 +295,10 @@ def run_b200(args):
     if sampler:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    # (read on rank 0 only and BEFORE the barrier: nvidia-smi takes ~1 s, and a rank that starts its timed steps late makes
+    # every other rank wait in the first exchange — the 2-GPU run of this round measured 0.855 instead of 0.404 s/step so)
     nvl0 = nvlink_counters(local) if (world > 1 and rank == 0) else None
+    barrier()
     e0.record()
     for i in range(args.steps):
         step(resident, i)
