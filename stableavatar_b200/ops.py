@@ -288,6 +288,29 @@ def conv3d_cl(x, w, bias, *, cout, k, out, res=None, out_mode=0, out_T_total=0, 
     return out
 
 
+def conv3d_halo_supported(cin, cout, k, stride_t=1, out_mode=0):
+    return bool(L.lib().sa_conv3d_halo_supported(cin, cout, k[0], k[1], k[2], stride_t, out_mode))
+
+
+def pack_conv_weight_halo(w5):
+    """[Cout, KT, KH, KW, Cin] -> bf16 [27][Cin / 8][Cout][8], the tcgen05 no-swizzle K-major layout sa_conv3d_halo_cl reads."""
+    cout, kt, kh, kw, cin = w5.shape
+    return w5.reshape(cout, kt * kh * kw, cin // 8, 8).permute(1, 2, 0, 3).to(torch.bfloat16).contiguous()
+
+
+def conv3d_halo_cl(x, w_packed, bias, *, cout, out, res=None, out_mode=0):
+    """3x3x3 'same' causal conv on channels-last bf16 x [Tout + 2, H, W, Cin] with halo staging — sa_conv3d_halo_cl."""
+    _need_cuda(x, w_packed)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w_packed.dtype == torch.bfloat16 and w_packed.is_contiguous()
+    assert bias.dtype == torch.float32 and out.is_contiguous() and (res is None or (res.is_contiguous() and res.dtype == torch.bfloat16))
+    Tin, H, W, Cin = x.shape
+    a = ConvArgs(inp=x.data_ptr(), w=w_packed.data_ptr(), bias=bias.data_ptr(), res=L.ptr(res), out=out.data_ptr(),
+                 Tout=Tin - 2, H=H, W=W, Cin=Cin, Cout=cout, KT=3, KH=3, KW=3, out_mode=out_mode, out_T_total=0, out_t0=0,
+                 pad_h=-1, pad_w=-1, stride_t=1)
+    L.check(L.lib().sa_conv3d_halo_cl(C.byref(a), L.stream_ptr()), "sa_conv3d_halo_cl")
+    return out
+
+
 def vae_rmsnorm_silu(x, gamma, out, silu=True):
     _need_cuda(x)
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and out.is_contiguous() and gamma.dtype == torch.float32

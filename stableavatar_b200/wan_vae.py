@@ -77,6 +77,8 @@ def _build_param_tree(root: nn.Module, shapes: dict):
 class _Conv:
     """One causal conv with its persistent input ring buffer [2 + Tmax, H, W, Cin] (two leading cache frames)."""
 
+    use_halo = True        # A/B switch of tools/vae_bench.py; the per-tap kernel computes the same convolution
+
     def __init__(self, weight, bias, dev, lead=None, stride_t=1, pad=None):
         if weight.dim() == 4:
             weight = weight.unsqueeze(2)
@@ -88,6 +90,10 @@ class _Conv:
         w = torch.zeros(cout_pad, kt, kh, kw, self.cin, device=dev, dtype=torch.float32)
         w[:cout, ..., :cin] = weight.to(dev, torch.float32).permute(0, 2, 3, 4, 1)
         self.w = w.reshape(cout_pad, -1).to(torch.bfloat16).contiguous()
+        # the convs that carry the decoder / encoder (3x3x3, 96 / 192 output channels) take the halo-staged kernel
+        self.halo = (self.use_halo and lead is None and stride_t == 1 and pad is None and cout_pad == cout and
+                     ops.conv3d_halo_supported(self.cin, cout, (kt, kh, kw)))
+        self.w_halo = ops.pack_conv_weight_halo(w.to(torch.bfloat16)) if self.halo else None
         self.bias = bias.to(dev, torch.float32).contiguous()
         self.buf = None
 
@@ -106,8 +112,11 @@ class _Conv:
 
     def run(self, tc, out, res=None, keep_cache=True, **kw):
         lead = self.lead
-        ops.conv3d_cl(self.buf[:lead + tc], self.w, self.bias, cout=self.cout, k=self.k, out=out, res=res, pad=self.pad,
-                      stride_t=self.stride_t, **kw)
+        if self.halo and kw.get("out_mode", 0) in (0, 1) and set(kw) <= {"out_mode"}:
+            ops.conv3d_halo_cl(self.buf[:lead + tc], self.w_halo, self.bias, cout=self.cout, out=out, res=res, **kw)
+        else:
+            ops.conv3d_cl(self.buf[:lead + tc], self.w, self.bias, cout=self.cout, k=self.k, out=out, res=res, pad=self.pad,
+                          stride_t=self.stride_t, **kw)
         if keep_cache and lead:                      # new cache = last two frames of [old cache, x]  (wan_vae.py:208-220)
             for j in range(lead):
                 self.buf[j].copy_(self.buf[tc + j])

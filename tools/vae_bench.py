@@ -4,7 +4,12 @@ import time
 import torch
 sys.path.insert(0, ".")
 from stableavatar_b200 import synth, _lib
+from stableavatar_b200 import wan_vae
 from stableavatar_b200.wan_vae import AutoencoderKLWan
+
+if "--no-halo" in sys.argv:            # A/B: every conv on the per-tap kernel
+    wan_vae._Conv.use_halo = False
+    sys.argv.remove("--no-halo")
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 21
 h, w = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (60, 104)
