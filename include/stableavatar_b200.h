@@ -244,10 +244,11 @@ typedef struct {
   int32_t pad_h, pad_w, stride_t;
 } sa_conv_args;
 int sa_conv3d_cl(const sa_conv_args* args, sa_stream_t stream);
-/* The same convolution for the shapes that carry the decoder (3x3x3, 'same' padding, stride 1, Cout 96 with Cin % 48 == 0 or
- * Cout 192 with Cin % 96 == 0, out_mode 0 / 1; sa_conv3d_halo_supported says which): the input halo of an output tile is
- * staged once in shared memory and the 9 spatial taps are shared-memory descriptor offsets; weights are shared by 2-4
- * output tiles. args->w is the weight PRE-PACKED as bf16 [27 taps (kt,kh,kw)][Cin / 8][Cout][8] (wan_vae.py:20-39). */
+/* The same convolution for the shapes that carry the decoder and encoder (KT x 3 x 3 with KT = 1 or 3, 'same' padding,
+ * stride 1, Cout 96 with Cin % 48 == 0 or Cout 192 / 384 with Cin % 96 == 0, out_mode 0 / 1; sa_conv3d_halo_supported says
+ * which): the input halo of an output tile is staged once in shared memory and the 9 spatial taps are shared-memory
+ * descriptor offsets; weights are shared by 2-4 output tiles. args->w is the weight PRE-PACKED as bf16
+ * [Cout / BN][KT*9 taps (kt,kh,kw)][Cin / 8][BN][8], BN = 96 for Cout 96, else 192 (wan_vae.py:20-39, 69-143). */
 int sa_conv3d_halo_supported(int32_t Cin, int32_t Cout, int32_t KT, int32_t KH, int32_t KW, int32_t stride_t, int32_t out_mode);
 int sa_conv3d_halo_cl(const sa_conv_args* args, sa_stream_t stream);
 

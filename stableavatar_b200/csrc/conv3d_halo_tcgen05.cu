@@ -35,6 +35,7 @@ constexpr int NUM_THREADS = 320;
 constexpr int PRODUCERS = 128;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_DATA = 225 * 1024;
+constexpr int BIAS_BYTES = 2048;               // up to 512 output channels, the tail of the data region
 constexpr int SMEM_BYTES = SMEM_DATA + 256 + 1024;
 
 struct Params {
@@ -43,11 +44,12 @@ struct Params {
   const float* bias;
   const __nv_bfloat16* res;
   void* out;
-  int Tout, H, W, Cin, Cout;
+  int Tout, H, W, Cin, Cout, KT;
   int ncg;                 // channel groups per time tap
+  int passes_per_nt;       // passes of one Cout tile (BN output channels); pass = nt * passes_per_nt + tile group
   int w_stage_bytes, w_stages;
   int tiles_w, tiles_h, num_tiles, num_passes;
-  int out_mode;
+  int out_mode, out_T_total, out_t0;
 };
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
@@ -61,6 +63,16 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                : "memory");
 }
 
+__device__ __forceinline__ void st_global_32B(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                              uint32_t g, uint32_t h) {   // one full 32-byte sector per thread
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+               "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // G output tiles per pass, NCH 16-byte channel chunks (8 channels each) per halo stage, BN = Cout
 template <int G, int NCH, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Params p) {
@@ -72,6 +84,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Param
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_halo = smem;
   uint8_t* s_w = smem + HALO_BUFS * HALO_STAGE;
+  float* s_bias = reinterpret_cast<float*>(smem + SMEM_DATA - BIAS_BYTES);   // [Cout]
   uint64_t* hfull = reinterpret_cast<uint64_t*>(smem + SMEM_DATA);
   uint64_t* hempty = hfull + HALO_BUFS;
   uint64_t* wfull = hempty + HALO_BUFS;
@@ -114,13 +127,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Param
     h0 = (r / p.tiles_w) * TH;
     w0 = (r % p.tiles_w) * TW;
   };
-  const int stages_per_pass = 3 * p.ncg;            // halo stages: (kt, channel group)
+  const int stages_per_pass = p.KT * p.ncg;         // halo stages: (kt, channel group)
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer: one bulk copy per (kt, cg, tap)
     if (elect_one()) {
       uint32_t wit = 0;
       for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x) {
+        const int nt = pass / p.passes_per_nt;
         for (int hs = 0; hs < stages_per_pass; ++hs) {
           const int kt = hs / p.ncg, cg = hs % p.ncg;
           for (int tap = 0; tap < 9; ++tap, ++wit) {
@@ -128,7 +142,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Param
             const uint32_t ph = (wit / p.w_stages) & 1;
             mbar_wait(&wempty[s], ph ^ 1, 0xb100 | s);
             mbar_arrive_expect_tx(&wfull[s], p.w_stage_bytes);
-            const long long off = ((long long)((kt * 9 + tap) * (p.Cin / 8) + cg * NCH) * BN) * 8;   // elements
+            const long long off = ((long long)(((nt * p.KT + kt) * 9 + tap) * (p.Cin / 8) + cg * NCH) * BN) * 8;   // elements
             bulk_load(smem_u32(s_w + s * p.w_stage_bytes), p.w + off, p.w_stage_bytes, &wfull[s]);
           }
         }
@@ -171,16 +185,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Param
       }
     }
   } else if (warp < 6) {
-    // ------------------------------------------------------------ epilogue: one output position per thread
+    // ------------------------------------------------------------ epilogue: one output position per thread. The
+    // accumulators of a pass are single-buffered (4 x 96 or 2 x 192 columns), so the next pass's MMAs wait for this code:
+    // a tile's accumulator is pulled into registers 96 columns at a time and handed back (tempty) BEFORE bias / residual /
+    // packing / stores run — the MMA issuer sat 32 % of its time on tempty when the hand-back came after the stores.
     const int q = warp & 3;
+    const int etid = threadIdx.x - 64;
+    for (int i = etid; i < p.Cout; i += 128) s_bias[i] = p.bias[i];
+    named_bar_sync(1, 128);
     uint32_t pcount = 0;
     for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x, ++pcount) {
       mbar_wait(tfull, pcount & 1, 0xb500);
       tc_fence_after();
       const int r = q * 32 + lane;
+      const int nt = pass / p.passes_per_nt, grp = pass % p.passes_per_nt;
 #pragma unroll 1
       for (int g = 0; g < G; ++g) {
-        const int tile = pass * G + g;
+        const int tile = grp * G + g;
         int t = 0, h0 = 0, w0 = 0;
         const bool tile_ok = tile < p.num_tiles;
         if (tile_ok) decode(tile, t, h0, w0);
@@ -188,52 +209,77 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Param
         const bool ok = tile_ok && h < p.H && w < p.W;
         const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + g * BN;
         const long long pos = ((long long)t * p.H + h) * p.W + w;
-#pragma unroll 1
-        for (int c = 0; c < BN / 16; ++c) {
-          uint32_t rr[16];
+        if constexpr (BN == 16) {
+          // the decoder head (96 -> 3): fp32 planar [Cout, T_total, H, W], clamped to [-1, 1] (wan_vae.py:668)
+          uint32_t acc[16];
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]),
-                "=r"(rr[8]), "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
-              : "r"(t_row + c * 16)
+              : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
+                "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]), "=r"(acc[15])
+              : "r"(t_row)
               : "memory");
           tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[g]);
+          if (ok) {
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < p.Cout)
+                o[(((long long)i * p.out_T_total + p.out_t0 + t) * p.H + h) * p.W + w] =
+                    fminf(fmaxf(__uint_as_float(acc[i]) + s_bias[i], -1.f), 1.f);
+          }
+        } else
+#pragma unroll 1
+        for (int half = 0; half < BN / 96; ++half) {
+          uint32_t acc[96];
+          tmem_ld_x32(t_row + half * 96, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+          tmem_ld_x32(t_row + half * 96 + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+          tmem_ld_x32(t_row + half * 96 + 64, *reinterpret_cast<uint32_t(*)[32]>(&acc[64]));
+          tmem_ld_wait();
+          if (half == BN / 96 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[g]);
+          }
           if (!ok) continue;
-          const int n0 = c * 16;
-          float y[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(rr[i]) + __ldg(p.bias + n0 + i);
-          long long off;
-          if (p.out_mode == 1) {  // channels [0,C) -> frame 2t, [C,2C) -> frame 2t+1 (wan_vae.py:137-140)
-            const int C = BN >> 1;
-            off = ((((long long)(2 * t + n0 / C)) * p.H + h) * p.W + w) * C + n0 % C;
-          } else {
-            off = pos * BN + n0;
-          }
-          if (p.res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
-            const uint4 u0 = rp[0], u1 = rp[1];
-            const __nv_bfloat162* hh0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
-            const __nv_bfloat162* hh1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+          for (int c = 0; c < 6; ++c) {
+            const int n0 = nt * BN + half * 96 + c * 16;          // output channel
+            float y[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 f0 = __bfloat1622float2(hh0[i]), f1 = __bfloat1622float2(hh1[i]);
-              y[2 * i] += f0.x; y[2 * i + 1] += f0.y;
-              y[8 + 2 * i] += f1.x; y[8 + 2 * i + 1] += f1.y;
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 bb = *reinterpret_cast<const float4*>(&s_bias[n0 + i4 * 4]);
+              y[i4 * 4 + 0] = __uint_as_float(acc[c * 16 + i4 * 4 + 0]) + bb.x;
+              y[i4 * 4 + 1] = __uint_as_float(acc[c * 16 + i4 * 4 + 1]) + bb.y;
+              y[i4 * 4 + 2] = __uint_as_float(acc[c * 16 + i4 * 4 + 2]) + bb.z;
+              y[i4 * 4 + 3] = __uint_as_float(acc[c * 16 + i4 * 4 + 3]) + bb.w;
             }
+            long long off;
+            if (p.out_mode == 1) {  // channels [0,C) -> frame 2t, [C,2C) -> frame 2t+1 (wan_vae.py:137-140)
+              const int C = p.Cout >> 1;
+              off = ((((long long)(2 * t + n0 / C)) * p.H + h) * p.W + w) * C + n0 % C;
+            } else {
+              off = pos * p.Cout + n0;
+            }
+            if (p.res) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
+              const uint4 u0 = rp[0], u1 = rp[1];
+              const __nv_bfloat162* hh0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
+              const __nv_bfloat162* hh1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f0 = __bfloat1622float2(hh0[i]), f1 = __bfloat1622float2(hh1[i]);
+                y[2 * i] += f0.x; y[2 * i + 1] += f0.y;
+                y[8 + 2 * i] += f1.x; y[8 + 2 * i + 1] += f1.y;
+              }
+            }
+            st_global_32B(reinterpret_cast<__nv_bfloat16*>(p.out) + off, pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                          pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]), pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]),
+                          pack_bf16x2(y[12], y[13]), pack_bf16x2(y[14], y[15]));
           }
-          uint4 v0, v1;
-          v0.x = pack_bf16x2(y[0], y[1]);   v0.y = pack_bf16x2(y[2], y[3]);
-          v0.z = pack_bf16x2(y[4], y[5]);   v0.w = pack_bf16x2(y[6], y[7]);
-          v1.x = pack_bf16x2(y[8], y[9]);   v1.y = pack_bf16x2(y[10], y[11]);
-          v1.z = pack_bf16x2(y[12], y[13]); v1.w = pack_bf16x2(y[14], y[15]);
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
-          op[0] = v0;
-          op[1] = v1;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[g]);
       }
     }
   } else {
@@ -245,7 +291,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Param
       bool tok[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        const int tile = pass * G + g;
+        const int tile = (pass % p.passes_per_nt) * G + g;
         tok[g] = tile < p.num_tiles;
         tt[g] = th0[g] = tw0[g] = 0;
         if (tok[g]) decode(tile, tt[g], th0[g], tw0[g]);
@@ -288,9 +334,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Param
 
 extern "C" int sa_conv3d_halo_supported(int32_t Cin, int32_t Cout, int32_t KT, int32_t KH, int32_t KW, int32_t stride_t,
                                         int32_t out_mode) {
-  if (KT != 3 || KH != 3 || KW != 3 || stride_t > 1 || out_mode < 0 || out_mode > 1) return 0;
+  if ((KT != 3 && KT != 1) || KH != 3 || KW != 3 || stride_t > 1 || out_mode < 0 || out_mode > 2) return 0;
+  if (out_mode == 2) return Cout <= 16 && Cin % 48 == 0;       // the video head: weights padded to 16 output channels
   if (Cout == 96) return Cin % 48 == 0;
-  if (Cout == 192) return Cin % 96 == 0;
+  if (Cout > 0 && Cout % 192 == 0 && Cout <= 384) return Cin % 96 == 0;
   return 0;
 }
 
@@ -302,8 +349,8 @@ extern "C" int sa_conv3d_halo_cl(const sa_conv_args* a, sa_stream_t stream_) {
   if (a->Tout <= 0 || a->H <= 0 || a->W <= 0) { set_error("sa_conv3d_halo_cl: bad dims"); return SA_ERR_BAD_ARG; }
   if (!sa_conv3d_halo_supported(a->Cin, a->Cout, a->KT, a->KH, a->KW, a->stride_t, a->out_mode) ||
       (a->pad_h >= 0 && a->pad_h != 1) || (a->pad_w >= 0 && a->pad_w != 1)) {
-    set_error("sa_conv3d_halo_cl: only 3x3x3 'same' stride-1 convs with Cout 96 (Cin %% 48 == 0) or 192 (Cin %% 96 == 0), "
-              "out_mode 0 / 1; got Cin %d Cout %d K %dx%dx%d", a->Cin, a->Cout, a->KT, a->KH, a->KW);
+    set_error("sa_conv3d_halo_cl: only (1|3)x3x3 'same' stride-1 convs with Cout 96 (Cin %% 48 == 0) or 192 / 384 (Cin %% 96 == 0), "
+              "out_mode 0 / 1 (or Cout <= 16 with out_mode 2); got Cin %d Cout %d K %dx%dx%d", a->Cin, a->Cout, a->KT, a->KH, a->KW);
     return SA_ERR_UNSUPPORTED;
   }
   Params p;
@@ -312,21 +359,27 @@ extern "C" int sa_conv3d_halo_cl(const sa_conv_args* a, sa_stream_t stream_) {
   p.bias = reinterpret_cast<const float*>(a->bias);
   p.res = reinterpret_cast<const __nv_bfloat16*>(a->res);
   p.out = a->out;
-  p.Tout = a->Tout; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout;
+  p.Tout = a->Tout; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout; p.KT = a->KT;
   p.tiles_w = (a->W + TW - 1) / TW; p.tiles_h = (a->H + TH - 1) / TH;
   p.num_tiles = a->Tout * p.tiles_w * p.tiles_h;
   p.out_mode = a->out_mode;
-  const int G = a->Cout == 96 ? 4 : 2, nch = a->Cout == 96 ? 6 : 12;
+  const bool head = a->out_mode == 2;
+  const int G = (head || a->Cout == 96) ? 4 : 2, nch = (head || a->Cout == 96) ? 6 : 12, bn = head ? 16 : (a->Cout == 96 ? 96 : 192);
+  p.out_T_total = a->out_T_total; p.out_t0 = a->out_t0;
   p.ncg = a->Cin / (nch * 8);
-  p.num_passes = (p.num_tiles + G - 1) / G;
-  p.w_stage_bytes = nch * 8 * a->Cout * 2;
+  p.passes_per_nt = (p.num_tiles + G - 1) / G;
+  p.num_passes = p.passes_per_nt * (head ? 1 : a->Cout / bn);
+  p.w_stage_bytes = nch * 8 * bn * 2;
   const int halo_bytes = HALO_BUFS * G * nch * PLANE;
-  p.w_stages = (SMEM_DATA - halo_bytes) / p.w_stage_bytes;
+  p.w_stages = (SMEM_DATA - BIAS_BYTES - halo_bytes) / p.w_stage_bytes;
   if (p.w_stages > MAX_W_STAGES) p.w_stages = MAX_W_STAGES;
   if (p.w_stages < 2) { set_error("sa_conv3d_halo_cl: shared memory budget"); return SA_ERR_UNSUPPORTED; }
   const int grid = p.num_passes < sm_count() ? p.num_passes : sm_count();
   int rc;
-  if (a->Cout == 96) {
+  if (head) {
+    if ((rc = ensure_dyn_smem(conv3d_halo_kernel<4, 6, 16>, SMEM_BYTES, "conv3d_halo_kernel"))) return rc;
+    conv3d_halo_kernel<4, 6, 16><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  } else if (a->Cout == 96) {
     if ((rc = ensure_dyn_smem(conv3d_halo_kernel<4, 6, 96>, SMEM_BYTES, "conv3d_halo_kernel"))) return rc;
     conv3d_halo_kernel<4, 6, 96><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
   } else {

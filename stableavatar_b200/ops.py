@@ -293,19 +293,24 @@ def conv3d_halo_supported(cin, cout, k, stride_t=1, out_mode=0):
 
 
 def pack_conv_weight_halo(w5):
-    """[Cout, KT, KH, KW, Cin] -> bf16 [27][Cin / 8][Cout][8], the tcgen05 no-swizzle K-major layout sa_conv3d_halo_cl reads."""
+    """[Cout, KT, KH, KW, Cin] -> bf16 [Cout / BN][taps][Cin / 8][BN][8] (BN = 96 or 192 output channels per tile), the tcgen05
+    no-swizzle K-major layout sa_conv3d_halo_cl reads."""
     cout, kt, kh, kw, cin = w5.shape
-    return w5.reshape(cout, kt * kh * kw, cin // 8, 8).permute(1, 2, 0, 3).to(torch.bfloat16).contiguous()
+    if cout <= 16:                                     # the video head: one 16-channel tile, rows >= cout zero
+        w5 = torch.cat([w5, w5.new_zeros(16 - cout, kt, kh, kw, cin)]) if cout < 16 else w5
+        cout = 16
+    bn = cout if cout in (16, 96) else 192
+    return w5.reshape(cout // bn, bn, kt * kh * kw, cin // 8, 8).permute(0, 2, 3, 1, 4).to(torch.bfloat16).contiguous()
 
 
-def conv3d_halo_cl(x, w_packed, bias, *, cout, out, res=None, out_mode=0):
-    """3x3x3 'same' causal conv on channels-last bf16 x [Tout + 2, H, W, Cin] with halo staging — sa_conv3d_halo_cl."""
+def conv3d_halo_cl(x, w_packed, bias, *, cout, out, res=None, out_mode=0, kt=3, out_T_total=0, out_t0=0):
+    """(kt)x3x3 'same' causal conv on channels-last bf16 x [Tout + kt - 1, H, W, Cin] with halo staging — sa_conv3d_halo_cl."""
     _need_cuda(x, w_packed)
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and w_packed.dtype == torch.bfloat16 and w_packed.is_contiguous()
     assert bias.dtype == torch.float32 and out.is_contiguous() and (res is None or (res.is_contiguous() and res.dtype == torch.bfloat16))
     Tin, H, W, Cin = x.shape
     a = ConvArgs(inp=x.data_ptr(), w=w_packed.data_ptr(), bias=bias.data_ptr(), res=L.ptr(res), out=out.data_ptr(),
-                 Tout=Tin - 2, H=H, W=W, Cin=Cin, Cout=cout, KT=3, KH=3, KW=3, out_mode=out_mode, out_T_total=0, out_t0=0,
+                 Tout=Tin - (kt - 1), H=H, W=W, Cin=Cin, Cout=cout, KT=kt, KH=3, KW=3, out_mode=out_mode, out_T_total=out_T_total, out_t0=out_t0,
                  pad_h=-1, pad_w=-1, stride_t=1)
     L.check(L.lib().sa_conv3d_halo_cl(C.byref(a), L.stream_ptr()), "sa_conv3d_halo_cl")
     return out

@@ -78,6 +78,7 @@ class _Conv:
     """One causal conv with its persistent input ring buffer [2 + Tmax, H, W, Cin] (two leading cache frames)."""
 
     use_halo = True        # A/B switch of tools/vae_bench.py; the per-tap kernel computes the same convolution
+    generation = 0         # bumped whenever any ring buffer is (re)allocated: captured CUDA graphs hold their addresses
 
     def __init__(self, weight, bias, dev, lead=None, stride_t=1, pad=None):
         if weight.dim() == 4:
@@ -91,9 +92,11 @@ class _Conv:
         w[:cout, ..., :cin] = weight.to(dev, torch.float32).permute(0, 2, 3, 4, 1)
         self.w = w.reshape(cout_pad, -1).to(torch.bfloat16).contiguous()
         # the convs that carry the decoder / encoder (3x3x3, 96 / 192 output channels) take the halo-staged kernel
+        self.halo_head = self.use_halo and lead is None and stride_t == 1 and pad is None and \
+            ops.conv3d_halo_supported(self.cin, cout, (kt, kh, kw), out_mode=2)            # Cout <= 16: the video head
         self.halo = (self.use_halo and lead is None and stride_t == 1 and pad is None and cout_pad == cout and
                      ops.conv3d_halo_supported(self.cin, cout, (kt, kh, kw)))
-        self.w_halo = ops.pack_conv_weight_halo(w.to(torch.bfloat16)) if self.halo else None
+        self.w_halo = ops.pack_conv_weight_halo(w[:cout].to(torch.bfloat16)) if (self.halo or self.halo_head) else None
         self.bias = bias.to(dev, torch.float32).contiguous()
         self.buf = None
 
@@ -101,6 +104,7 @@ class _Conv:
         lead = self.lead
         if self.buf is None or self.buf.shape != (lead + tmax, H, W, self.cin):
             self.buf = torch.zeros(lead + tmax, H, W, self.cin, device=dev, dtype=torch.bfloat16)
+            _Conv.generation += 1
         else:
             self.buf[:lead].zero_()
         return self
@@ -112,8 +116,12 @@ class _Conv:
 
     def run(self, tc, out, res=None, keep_cache=True, **kw):
         lead = self.lead
-        if self.halo and kw.get("out_mode", 0) in (0, 1) and set(kw) <= {"out_mode"}:
-            ops.conv3d_halo_cl(self.buf[:lead + tc], self.w_halo, self.bias, cout=self.cout, out=out, res=res, **kw)
+        # (small frames leave the halo kernel's coarse work units — 2-4 output tiles x 96 / 192 channels — short of one wave)
+        big = tc * ((self.buf.shape[1] + 15) // 16) * ((self.buf.shape[2] + 7) // 8) * max(1, self.cout // 192) >= 592
+        if self.halo_head and big and kw.get("out_mode", 0) == 2 and res is None:
+            ops.conv3d_halo_cl(self.buf[:lead + tc], self.w_halo, self.bias, cout=self.cout, out=out, kt=self.k[0], **kw)
+        elif self.halo and big and kw.get("out_mode", 0) in (0, 1) and set(kw) <= {"out_mode"}:
+            ops.conv3d_halo_cl(self.buf[:lead + tc], self.w_halo, self.bias, cout=self.cout, out=out, res=res, kt=self.k[0], **kw)
         else:
             ops.conv3d_cl(self.buf[:lead + tc], self.w, self.bias, cout=self.cout, k=self.k, out=out, res=res, pad=self.pad,
                           stride_t=self.stride_t, **kw)
@@ -138,6 +146,8 @@ class AutoencoderKLWan(nn.Module):
         self.scale = [self.mean, 1.0 / self.std]
         self._prep = self._prep_enc = None
         self._pp_group, self._pp_world, self._pp_rank = None, 1, 0
+        self.use_cuda_graph = True        # steady-state decode chunks replayed from one captured graph (single GPU)
+        self._dec_graph = self._dec_seen = None
 
     @property
     def dtype(self):
@@ -550,9 +560,38 @@ class AutoencoderKLWan(nn.Module):
         last = max(r for r in range(world) if ranges[r][1] > ranges[r][0])
         x_all = ops.vae_latent_in(z.contiguous(), p["wc"], p["bc"], p["mean"], p["std"], 32) if lo == 0 and hi > 0 else None
         t_out = 0
+        # Every chunk after the first has the same shapes and touches the same ring buffers: chunk 1 runs eagerly (it is also
+        # the first use of the temporal-upsampling kernels), chunk 2 is captured as ONE CUDA graph and replayed for the rest
+        # — ~80 kernel launches and ~60 cache copies per chunk leave the host, which was the decode's bottleneck once the
+        # convolutions got faster (wall 478 ms for 362 ms of kernels). The graph reads its latent frame from / writes its
+        # 4 video frames to static buffers.
+        # The graph is kept across decode() calls for as long as the ring buffers it addresses stay where they are
+        # (instantiating ~140 nodes costs 0.3-0.5 s, more than the decode).
+        # A shape is captured on its SECOND decode only: a one-off decode would pay more for the capture than it saves.
+        gkey = (h, w, str(dev), _Conv.generation, id(p))
+        use_graph = world == 1 and self.use_cuda_graph and T >= 4 and self._dec_seen == gkey
+        self._dec_seen = gkey
+        if use_graph and (self._dec_graph is None or self._dec_graph[0] != gkey):
+            self._dec_graph = None
         for i in range(T):
             shapes = self._unit_shapes(h, w, i)
-            if hi > lo:
+            if use_graph and i >= 2:
+                nf = shapes[n_units - 1][0]
+                if self._dec_graph is None:
+                    gin = x_all[i:i + 1].clone()
+                    gvid = torch.empty(3, nf, video.shape[2], video.shape[3], device=dev, dtype=torch.float32)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        a = gin
+                        for idx in range(n_units):
+                            a = self._run_unit(idx, a, i, gvid, 0)
+                    self._dec_graph = (gkey, graph, gin, gvid)
+                else:
+                    self._dec_graph[2].copy_(x_all[i:i + 1])
+                _, graph, gin, gvid = self._dec_graph
+                graph.replay()
+                video[:, t_out:t_out + nf].copy_(gvid)
+            elif hi > lo:
                 if lo == 0:
                     a = x_all[i:i + 1]
                 else:

@@ -235,21 +235,23 @@ def test_fused_cross_attention_plain_sets_and_accumulate(ops):
 
 @pytest.mark.parametrize("cin,cout,T,H,W,mode,with_res", [(96, 96, 2, 16, 8, 0, False), (96, 96, 3, 37, 21, 0, True),
                                                           (192, 192, 2, 40, 24, 0, True), (96, 192, 1, 16, 16, 1, False),
-                                                          (192, 96, 2, 33, 50, 0, False), (384, 192, 1, 20, 12, 0, True)])
-def test_halo_conv_vs_torch_conv3d(ops, cin, cout, T, H, W, mode, with_res):
+                                                          (192, 96, 2, 33, 50, 0, False), (384, 192, 1, 20, 12, 0, True),
+                                                          (192, 384, 2, 24, 16, 0, False), (384, 384, 1, 15, 26, 0, True)])
+@pytest.mark.parametrize("kt", [3, 1])
+def test_halo_conv_vs_torch_conv3d(ops, cin, cout, T, H, W, mode, with_res, kt):
     """sa_conv3d_halo_cl (input halo staged once, taps as descriptor offsets, weights shared by 2-4 tiles) against
     torch conv3d in fp32 on the same bf16 operands, and against the per-tap kernel sa_conv3d_cl it replaces: ragged tiles,
     residual add, the frame-interleaved output of the temporal upsampler, 1-4 channel groups."""
     g = torch.Generator(device="cuda").manual_seed(cin + cout + H)
-    x = torch.randn(T + 2, H, W, cin, device="cuda", generator=g).bfloat16()
-    w5 = (torch.randn(cout, 3, 3, 3, cin, device="cuda", generator=g) * (27 * cin) ** -0.5).bfloat16()
+    x = torch.randn(T + kt - 1, H, W, cin, device="cuda", generator=g).bfloat16()
+    w5 = (torch.randn(cout, kt, 3, 3, cin, device="cuda", generator=g) * (9 * kt * cin) ** -0.5).bfloat16()
     bias = torch.randn(cout, device="cuda", generator=g)
     oshape = (2 * T, H, W, cout // 2) if mode == 1 else (T, H, W, cout)
     res = torch.randn(oshape, device="cuda", generator=g).bfloat16() if with_res else None
-    assert ops.conv3d_halo_supported(cin, cout, (3, 3, 3), 1, mode)
+    assert ops.conv3d_halo_supported(cin, cout, (kt, 3, 3), 1, mode)
     out = ops.conv3d_halo_cl(x, ops.pack_conv_weight_halo(w5), bias, cout=cout, out=torch.empty(oshape, device="cuda", dtype=torch.bfloat16),
-                             res=res, out_mode=mode)
-    old = ops.conv3d_cl(x, w5.reshape(cout, -1).contiguous(), bias, cout=cout, k=(3, 3, 3),
+                             res=res, out_mode=mode, kt=kt)
+    old = ops.conv3d_cl(x, w5.reshape(cout, -1).contiguous(), bias, cout=cout, k=(kt, 3, 3),
                         out=torch.empty(oshape, device="cuda", dtype=torch.bfloat16), res=res, out_mode=mode)
     ref = torch.nn.functional.conv3d(x.float().permute(3, 0, 1, 2)[None], w5.float().permute(0, 4, 1, 2, 3), bias,
                                      padding=(0, 1, 1))[0].permute(1, 2, 3, 0)                       # [T, H, W, cout]
@@ -259,3 +261,22 @@ def test_halo_conv_vs_torch_conv3d(ops, cin, cout, T, H, W, mode, with_res):
         ref = ref + res.float()
     assert rel(out, ref) < 4e-3 and rel(old, ref) < 4e-3
     assert rel(out, old) < 3e-3
+
+
+def test_halo_conv_video_head_vs_per_tap_kernel(ops):
+    """Decoder head (96 -> 3, fp32 planar clamped output into a frame window of a longer video) on the halo kernel."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    T, H, W, cin, cout = 2, 40, 27, 96, 3
+    x = torch.randn(T + 2, H, W, cin, device="cuda", generator=g).bfloat16()
+    w5 = (torch.randn(cout, 3, 3, 3, cin, device="cuda", generator=g) * (27 * cin) ** -0.5 * 2).bfloat16()
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.3
+    assert ops.conv3d_halo_supported(cin, cout, (3, 3, 3), 1, 2)
+    new = torch.full((cout, 5, H, W), 9.0, device="cuda")
+    old = torch.full((cout, 5, H, W), 9.0, device="cuda")
+    ops.conv3d_halo_cl(x, ops.pack_conv_weight_halo(w5), bias, cout=cout, out=new, out_mode=2, out_T_total=5, out_t0=2)
+    w16 = torch.zeros(16, 27 * cin, device="cuda", dtype=torch.bfloat16)
+    w16[:cout] = w5.reshape(cout, -1)
+    ops.conv3d_cl(x, w16, bias, cout=cout, k=(3, 3, 3), out=old, out_mode=2, out_T_total=5, out_t0=2)
+    assert (new[:, :2] == 9.0).all() and (new[:, 4:] == 9.0).all()
+    assert (new[:, 2:4].abs() <= 1.0).all() and (new[:, 2:4].abs() == 1.0).any()           # the clamp is exercised
+    assert rel(new[:, 2:4], old[:, 2:4]) < 3e-3

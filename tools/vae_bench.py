@@ -7,6 +7,9 @@ from stableavatar_b200 import synth, _lib
 from stableavatar_b200 import wan_vae
 from stableavatar_b200.wan_vae import AutoencoderKLWan
 
+NO_GRAPH = "--no-graph" in sys.argv
+ENCODE = "--encode" in sys.argv
+sys.argv = [a for a in sys.argv if a not in ("--no-graph", "--encode")]
 if "--no-halo" in sys.argv:            # A/B: every conv on the per-tap kernel
     wan_vae._Conv.use_halo = False
     sys.argv.remove("--no-halo")
@@ -16,6 +19,7 @@ h, w = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (60, 104)
 vae = AutoencoderKLWan()
 vae.load_state_dict(synth.vae_state_dict(), strict=True)
 vae = vae.to("cuda")
+vae.use_cuda_graph = not NO_GRAPH
 z = synth.det_normal("vae_zfull", (1, 16, T, h, w)).cuda()
 out = vae.decode(z).sample          # warm-up (allocations, attribute setup)
 torch.cuda.synchronize()
@@ -32,7 +36,7 @@ print(f"vae decode T={T} {h}x{w}: {ms:.1f} ms (wall {1e3 * (time.perf_counter() 
       f"{_lib.launch_count} kernel launches, out {tuple(out.shape)} finite={bool(torch.isfinite(out).all())} "
       f"mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
 
-if "--encode" in sys.argv:
+if ENCODE:
     # Encode of the conditioning clip: x [1,3,1+4(T-1),8h,8w] -> latent [1,16,T,h,w]; 162.5 TFLOP at
     # the full size (81 x 480 x 832).
     vae.load_state_dict(synth.vae_state_dict(encoder=True), strict=True)
