@@ -190,7 +190,16 @@ extern "C" int sa_vae_rmsnorm_silu(const void* x, const void* gamma, void* out, 
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   const float* gp = reinterpret_cast<const float*>(gamma);
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
-  if (C <= 128) {
+  if (C == 96 || C == 192 || C == 384) {
+    // the decoder's widths: 3 chunks per lane, every lane busy (C / 24 lanes per position), three 16-byte loads in flight per
+    // thread — the one-chunk-per-lane form below keeps 4 of 16 lanes idle at C = 96 and reached 57 % of the HBM copy rate
+    const int lpr = C / 24;
+    const long long rpb = 8 * (32 / lpr);
+    const unsigned grid = (unsigned)((P + rpb - 1) / rpb);
+    if (lpr == 4) vae::rmsnorm_silu_kernel<4, 3><<<grid, 256, 0, stream>>>(xp, gp, op, P, C, silu);
+    else if (lpr == 8) vae::rmsnorm_silu_kernel<8, 3><<<grid, 256, 0, stream>>>(xp, gp, op, P, C, silu);
+    else vae::rmsnorm_silu_kernel<16, 3><<<grid, 256, 0, stream>>>(xp, gp, op, P, C, silu);
+  } else if (C <= 128) {
     const long long rows_per_block = 8 * 2;
     vae::rmsnorm_silu_kernel<16, 1><<<(unsigned)((P + rows_per_block - 1) / rows_per_block), 256, 0, stream>>>(xp, gp, op, P, C, silu);
   } else if (C <= 256) {

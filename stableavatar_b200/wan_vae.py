@@ -146,7 +146,10 @@ class AutoencoderKLWan(nn.Module):
         self.scale = [self.mean, 1.0 / self.std]
         self._prep = self._prep_enc = None
         self._pp_group, self._pp_world, self._pp_rank = None, 1, 0
-        self.use_cuda_graph = True        # steady-state decode chunks replayed from one captured graph (single GPU)
+        # Opt-in (long-lived serving processes): steady-state decode chunks replayed from one captured graph. It saves
+        # ~1.5 % of a decode (the decode is GPU-bound: 362 ms of kernels in 366 ms) but instantiating the graph costs
+        # 0.3-0.8 s the first time a shape is seen twice, more than a one-off caller ever gets back.
+        self.use_cuda_graph = False
         self._dec_graph = self._dec_seen = None
 
     @property
@@ -450,9 +453,9 @@ class AutoencoderKLWan(nn.Module):
 
     def _unit_costs(self, h, w):
         """Relative time of every unit for a steady-state chunk: conv FLOPs divided by a per-channel-width efficiency
-        guess taken from profiles/r01_kernels_ncu.txt (narrow convs are L2-operand-bound)."""
+        taken from tools/conv_bench.py on the halo-staged kernel (profiles/r02_conv_bench.log)."""
         costs = []
-        eff = lambda c: 0.6 if c <= 96 else (1.0 if c <= 192 else 1.1)  # noqa: E731  PFLOP/s-ish
+        eff = lambda c: 1.05 if c <= 96 else (1.35 if c <= 192 else 1.2)  # noqa: E731  PFLOP/s
         for (kind, d), (tc, H, W, C) in zip(self._units(), self._unit_shapes(h, w, 1)):
             pos = tc * H * W
             if kind == "res":
@@ -465,7 +468,7 @@ class AutoencoderKLWan(nn.Module):
                 f = 2 * t2 * 4 * H * W * 9 * C * (C // 2) + (2 * pos * 3 * C * 2 * C if kind == "up3d" else 0)
                 costs.append(f / eff(C // 2) + 8 * t2 * 4 * H * W * C * 40)
             elif kind == "head":
-                costs.append(2 * pos * 27 * C * 16 / 0.3 + 8 * pos * C * 40)
+                costs.append(2 * pos * 27 * C * 16 / 0.8 + 8 * pos * C * 40)
             else:
                 costs.append(2 * pos * 27 * 32 * self.dims[0])
         return costs

@@ -1,3 +1,4 @@
+"""Repeated full-size VAE decodes in one process: CUDA-graph replay on/off x halo-staged conv on/off, with clocks / power after each group."""
 import sys, subprocess, torch
 sys.path.insert(0, ".")
 from stableavatar_b200 import synth, wan_vae
