@@ -444,7 +444,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args, L),
-                       "detail": "30 blocks, CFG batch 3 + CFG/Euler, text 512 + CLIP 257 + audio 21x15; text/CLIP context encoded "
+                       "detail": f"{cfg['num_layers']} blocks, CFG batch 3 + CFG/Euler, text 512 + CLIP 257 + audio 21x15; text/CLIP context encoded "
                                  "once per clip (value) / once per step (e2e: its inputs change every step)",
                        "parallelism": f"sp{world}" if world > 1 else "single", "windows_per_step": Wn,
                        "l2_policy": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
