@@ -7,9 +7,9 @@ from stableavatar_b200 import synth, _lib
 from stableavatar_b200 import wan_vae
 from stableavatar_b200.wan_vae import AutoencoderKLWan
 
-NO_GRAPH = "--no-graph" in sys.argv
+GRAPH = "--graph" in sys.argv            # opt-in CUDA-graph replay of the steady-state chunk (the second decode captures)
 ENCODE = "--encode" in sys.argv
-sys.argv = [a for a in sys.argv if a not in ("--no-graph", "--encode")]
+sys.argv = [a for a in sys.argv if a not in ("--graph", "--encode")]
 if "--no-halo" in sys.argv:            # A/B: every conv on the per-tap kernel
     wan_vae._Conv.use_halo = False
     sys.argv.remove("--no-halo")
@@ -19,7 +19,7 @@ h, w = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (60, 104)
 vae = AutoencoderKLWan()
 vae.load_state_dict(synth.vae_state_dict(), strict=True)
 vae = vae.to("cuda")
-vae.use_cuda_graph = not NO_GRAPH
+vae.use_cuda_graph = GRAPH
 z = synth.det_normal("vae_zfull", (1, 16, T, h, w)).cuda()
 out = vae.decode(z).sample          # warm-up (allocations, attribute setup)
 torch.cuda.synchronize()
