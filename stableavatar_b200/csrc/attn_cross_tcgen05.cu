@@ -15,7 +15,8 @@
 //   * the TMA producer runs ahead across sets and items through a 3-stage ring, so the next item's first keys are in
 //     shared memory before its Q is;
 //   * the per-set results are summed in a shared-memory staging tile (bf16, every partial result rounded to bf16 before
-//     the bf16 add, set order text, image, audio — the arithmetic of three separate launches, bit for bit) and leave the
+//     the bf16 add, set order text, image, audio — the arithmetic of three separate launches; bit for bit for the plain
+//     sets, while the windowed set may pick a different one-in-eight of its keys for the FMA-pipe exponential) and leave the
 //     SM once per item as a TMA store (rows beyond q_len are clipped by the tensor map).
 //
 // The audio set is one 64-key step: the keys of the (at most 64 / A) consecutive windows that the item's 256 rows can
@@ -337,10 +338,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
         float pe[64];
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
-          float x0, x1;
-          unpack_f32x2(x2[t], x0, x1);
-          pe[2 * t] = ex2_approx(x0);
-          pe[2 * t + 1] = ex2_approx(x1);
+          SA_EXP2_PAIR(t, x2[t], pe[2 * t], pe[2 * t + 1]);   // the self-attention kernel's mix of MUFU and FMA-pipe exp2
         }
         uint64_t la = lsum2, lb = lsum2b, lc = pack_f32x2(0.f, 0.f), ld = pack_f32x2(0.f, 0.f);
 #pragma unroll

@@ -92,6 +92,7 @@ __device__ __forceinline__ void umma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint3
       : "memory");
 }
 
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                      const __grid_constant__ OutMaps tmap_o, const Params p) {
@@ -330,9 +331,10 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
         // exactly at the XU rate (8 cycles per warp instruction); the two softmax warps of an SM sub-partition share that
         // pipe, so a step costs each of them >= 1024 cycles of MUFU time — as much as the step's MMAs take on the tensor
         // pipe — plus ~400 cycles of barrier waits, TMEM load, row max and fences (in-kernel event trace,
-        // profiles/r02_attn_investigation.md). Round-2 variants that attacked this and did NOT pay, all measured in one
-        // process in randomised order against this body: exponentials partly on the FMA pipes (Cody-Waite + cubic, 6-25 %
-        // of them): +-3 %, inside the clock / power noise of a power-capped part; TMEM load + row max of S(u+1) hidden under
+        // profiles/r02_attn_investigation.md). One eighth of the exponentials therefore take the FMA / ALU pipes (exp2_pair):
+        // +3.5 % in a 30-round randomised rotation at B = 3 (r02_attn_ab_emulation_30rounds.log), while a quarter or more
+        // loses 1-2 % again (the extra ~10 instructions per pair cost issue slots and power). Round-2 variants that attacked
+        // the rest and did NOT pay, measured the same way: TMEM load + row max of S(u+1) hidden under
         // the exponentials of step u (224 registers through setmaxnreg): -8 ... -17 %; a shared 128-column score buffer
         // with 128-key steps handed between the two Q tiles: +-2 %. Sources: profiles/experiments/.
         uint64_t x2[32];
@@ -342,10 +344,7 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
         float pe[64];
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
-          float x0, x1;
-          unpack_f32x2(x2[t], x0, x1);
-          pe[2 * t] = ex2_approx(x0);
-          pe[2 * t + 1] = ex2_approx(x1);
+          SA_EXP2_PAIR(t, x2[t], pe[2 * t], pe[2 * t + 1]);
         }
         uint64_t la = lsum2, lb = lsum2b, lc = pack_f32x2(0.f, 0.f), ld = pack_f32x2(0.f, 0.f);
 #pragma unroll

@@ -251,6 +251,41 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return r;
 }
 
+// ---- softmax exponentials of the attention kernels (self and cross share the pattern, so their results stay bit-equal)
+// 2^x for a packed pair. EMULATE: on the FMA / ALU pipes instead of MUFU.EX2 (Cody-Waite split by the 1.5 * 2^23 magic add,
+// degree-3 minimax polynomial of 2^f on [-0.5, 0.5] — max relative error 7.5e-5, far inside the bf16 rounding of P — and
+// the integer part added into the exponent field). x <= the lazy-rescale threshold (8) by construction; the clamp keeps the exponent
+// add from wrapping for scores far below the running max.
+constexpr int kEmuPairsPer16 = 2;   // of every 16 packed pairs of exponentials, this many (evenly spread) skip the XU pipe
+template <bool EMULATE>
+__device__ __forceinline__ void exp2_pair(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  if constexpr (!EMULATE) {
+    p0 = ex2_approx(x0);
+    p1 = ex2_approx(x1);
+  } else {
+    const uint64_t xc = pack_f32x2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    const uint64_t t2 = add_f32x2(xc, pack_f32x2(12582912.0f, 12582912.0f));
+    const uint64_t n2 = add_f32x2(t2, pack_f32x2(-12582912.0f, -12582912.0f));
+    const uint64_t f2 = fma_f32x2(n2, pack_f32x2(-1.0f, -1.0f), xc);
+    uint64_t q2 = fma_f32x2(f2, pack_f32x2(0.0551716685f, 0.0551716685f), pack_f32x2(0.242611125f, 0.242611125f));
+    q2 = fma_f32x2(q2, f2, pack_f32x2(0.693260968f, 0.693260968f));
+    q2 = fma_f32x2(q2, f2, pack_f32x2(0.999928057f, 0.999928057f));
+    float t0, t1, q0, q1;
+    unpack_f32x2(t2, t0, t1);
+    unpack_f32x2(q2, q0, q1);
+    p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+    p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+  }
+}
+// exponential t of a 32-pair (64-key) softmax step
+#define SA_EXP2_PAIR(t, x2, p0, p1)                                                        \
+  do {                                                                                     \
+    if ((((t) * kEmuPairsPer16) & 15) < kEmuPairsPer16) exp2_pair<true>(x2, p0, p1);       \
+    else exp2_pair<false>(x2, p0, p1);                                                     \
+  } while (0)
+
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

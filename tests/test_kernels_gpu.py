@@ -203,7 +203,9 @@ def _cross_inputs(B, Lq, Hh, G, A, seed):
                                                      (520, 4, 0, 520)])       # 130-row groups: 4 windows inside one CTA
 def test_fused_cross_attention_equals_three_launches(ops, Lq, G, tok_offset, L_total):
     """sa_cross_attn3_d128 (text + image + windowed audio in one launch) against three sa_flash_attn_d128 launches with
-    accumulate (bit-identical by construction) and against fp32 torch SDPA per set."""
+    accumulate and against fp32 torch SDPA per set. The plain sets are bit-identical by construction (next test); the
+    windowed set sits at a different column offset of its 64-key step than a separate 15-key launch, so a different
+    one-in-eight of its keys takes the FMA-pipe exponential (relative error 7.5e-5 before the bf16 rounding of P)."""
     B, Hh, A = 2, 3, 15
     gs = L_total // G
     q, (kt, vt), (ki, vi), (ka, va) = _cross_inputs(B, Lq, Hh, G, A, 11)
@@ -216,7 +218,7 @@ def test_fused_cross_attention_equals_three_launches(ops, Lq, G, tok_offset, L_t
         ops.flash_attn(q[:, lo:hi], ka[:, g * A:(g + 1) * A], va[:, g * A:(g + 1) * A], out=want[:, lo:hi], accumulate=True)
         ref[:, lo:hi] += sdpa(q[:, lo:hi], ka[:, g * A:(g + 1) * A], va[:, g * A:(g + 1) * A])
     torch.cuda.synchronize()
-    assert torch.equal(got, want)
+    assert rel(got.float(), want.float()) < 1.5e-3 and (got.float() - want.float()).abs().max() <= 2.0 ** -6 * want.float().abs().max()
     assert rel(got.float(), ref) < 6e-3
 
 
