@@ -335,6 +335,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 6 ? 4 : (NCH <= 8
   const int tok = row % p.rows_per_batch + p.tok_offset;
   const bool rotate = p.freqs != nullptr && tok < p.F * p.H * p.W;
   const int pf = tok / (p.H * p.W), ph = (tok / p.W) % p.H, pw = tok % p.W;
+  // chunk ch = lane + 32 c sits at column (ch & 15) * 8 of its head: a lane meets the SAME four complex pairs in every
+  // chunk it owns, so their (cos, sin) are fetched once per row instead of once per chunk
+  float2 cs4[4];
+  if (rotate) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = (lane & 15) * 4 + i;
+      const int pos = j < 22 ? pf : (j < 43 ? ph : pw);
+      cs4[i] = __ldg(&p.freqs[pos * 64 + j]);
+    }
+  }
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int ch = lane + c * 32;
@@ -346,12 +357,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 6 ? 4 : (NCH <= 8
 #pragma unroll
     for (int i = 0; i < 8; ++i) y[i] = bf16_round(bf16_round(y[i] * rinv) * w[i]);
     if (rotate) {
-      const int j0 = (col & 127) >> 1;  // first complex pair of this chunk inside its head
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int j = j0 + i;
-        const int pos = j < 22 ? pf : (j < 43 ? ph : pw);
-        const float2 cs = __ldg(&p.freqs[pos * 64 + j]);
+        const float2 cs = cs4[i];
         const float a = y[2 * i], b = y[2 * i + 1];
         y[2 * i] = a * cs.x - b * cs.y;
         y[2 * i + 1] = a * cs.y + b * cs.x;
@@ -415,6 +423,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 6 ? 4 : (NCH <= 8
   const int s_me = p.rank % p.qs;
   const long long q_row = ((long long)b * (p.P / p.qs) + p.rank / p.qs) * p.Ll + t_loc;   // row index inside q_recv
   const long long kv_row = ((long long)b * p.P + p.rank) * p.Ll + t_loc;                  // row index inside kv_recv
+  float2 cs4[4];   // the four complex pairs this lane meets in every chunk it owns (see rmsnorm_rope_kernel)
+  if (rotate) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = (lane & 15) * 4 + i;
+      const int pos = j < 22 ? pf : (j < 43 ? ph : pw);
+      cs4[i] = __ldg(&p.freqs[pos * 64 + j]);
+    }
+  }
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int ch = lane + c * 32;
@@ -428,12 +445,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NCH <= 6 ? 4 : (NCH <= 8
 #pragma unroll
       for (int i = 0; i < 8; ++i) y[i] = bf16_round(bf16_round(y[i] * rinv) * w[i]);
       if (rotate) {
-        const int j0 = (col & 127) >> 1;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int j = j0 + i;
-          const int pos = j < 22 ? pf : (j < 43 ? ph : pw);
-          const float2 cs = __ldg(&p.freqs[pos * 64 + j]);
+          const float2 cs = cs4[i];
           const float a = y[2 * i], bb = y[2 * i + 1];
           y[2 * i] = a * cs.x - bb * cs.y;
           y[2 * i + 1] = a * cs.y + bb * cs.x;
