@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant__ CUtensorMap tv0,
                   const __grid_constant__ CUtensorMap tk1, const __grid_constant__ CUtensorMap tv1,
                   const __grid_constant__ CUtensorMap tk2, const __grid_constant__ CUtensorMap tv2,
-                  const __grid_constant__ CUtensorMap tmap_o, const Params p) {
+                  const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_q, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sKV = smem;                                   // [STAGES][K tile | V tile]
@@ -92,7 +92,9 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
   uint64_t* o_final = pv_done + 2;          // [2]  one completion per key set: the set's accumulator is complete
   uint64_t* q_ready = o_final + 2;          // [2]  one completion per item: Q tile i stored in TMEM
   uint64_t* o_free = q_ready + 2;           // [2]  one completion per key set: its epilogue has O_i in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* q_full = o_free + 2;            // [2]  one completion per item: Q tile i has landed in tile i's P buffers (TMA)
+  uint64_t* res_full = q_full + 2;          // [2]  one completion per item: the residual tile has landed in the staging tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,6 +104,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
     tma_prefetch_desc(&tk0);
     tma_prefetch_desc(&tv0);
     tma_prefetch_desc(&tmap_o);
+    tma_prefetch_desc(&tmap_q);
   }
   if (warp == 9) {
     if (lane == 0) {
@@ -116,6 +119,8 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
         mbar_init(&o_final[i], 1);
         mbar_init(&q_ready[i], 4);
         mbar_init(&o_free[i], 4);
+        mbar_init(&q_full[i], 1);
+        mbar_init(&res_full[i], 1);
       }
       for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
       fence_barrier_init();
@@ -160,26 +165,28 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
     // ------------------------------------------------------------ MMA issuers, one warp per Q tile
     if (elect_one()) {
       const int i = warp - 9;
-      const uint32_t idesc_qk = umma_idesc_bf16(BQ, SUB, 0, 0);  // A = Q (TMEM), B = 64 keys of K (K-major)
-      const uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);    // A = P (smem, K-major), B = V (MN-major)
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, SUB, 0, 0);  // A = Q (TMEM), B = 64 keys of K (K-major)
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);    // A = P (smem, K-major), B = V (MN-major)
+      // descriptors as in attn_self_tcgen05.cu: a 32-bit low word (address >> 4 | LBO) advanced by constants, one constant
+      // high word (SBO 1024, version 1, SWIZZLE_128B) — with 8 + 5 + 1 key steps per item this thread's serial path is on
+      // the critical chain at every item and set boundary
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (kSwz128 << 29);
+      const uint32_t k_lo0 = ((smem_u32(sKV) & 0x3ffff) >> 4) | (1u << 16);
+      const uint32_t v_lo0 = ((smem_u32(sKV + KV_TILE) & 0x3ffff) >> 4) | (uint32_t(KV_PANEL >> 4) << 16);
+      const uint32_t p_lo0 = ((smem_u32(sP + i * 2 * P_BYTES) & 0x3ffff) >> 4) | (1u << 16);
+      const uint32_t tSi = tmem_base + 128 + i * SUB, tQi = tmem_base + i * 64, tOi = tmem_base + 256 + i * 128;
       auto issue_S = [&](int U) {
-        const uint32_t ka = smem_u32(sKV + (U % STAGES) * STAGE_BYTES);
+        const uint32_t k_lo = k_lo0 + (U % STAGES) * (STAGE_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 2) * KV_PANEL + (k & 3) * 32;
-          umma_ts(tmem_base + 128 + i * SUB, tmem_base + i * 64 + k * 8, umma_smem_desc(ka + off, 16, 1024, kSwz128),
-                  idesc_qk, k != 0);
-        }
+        for (int k = 0; k < D / 16; ++k)
+          umma_ts_lh(tSi, tQi + k * 8, k_lo + (k >> 2) * (KV_PANEL >> 4) + (k & 3) * 2, DESC_HI, idesc_qk, k != 0);
         umma_commit(&s_full[i]);
       };
       auto issue_PV = [&](int U, bool first) {
-        const uint32_t va = smem_u32(sKV + (U % STAGES) * STAGE_BYTES + KV_TILE);
-        const uint32_t pa = smem_u32(sP + (i * 2 + (U & 1)) * P_BYTES);
+        const uint32_t v_lo = v_lo0 + (U % STAGES) * (STAGE_BYTES >> 4), p_lo = p_lo0 + (U & 1) * (P_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < SUB / 16; ++k) {
-          umma_ss(tmem_base + 256 + i * 128, umma_smem_desc(pa + k * 32, 16, 1024, kSwz128),
-                  umma_smem_desc(va + k * 2048, KV_PANEL, 1024, kSwz128), idesc_pv, (!first || k != 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < SUB / 16; ++k)
+          umma_ss_lh(tOi, p_lo + k * 2, DESC_HI, v_lo + k * (2048 >> 4), DESC_HI, idesc_pv, (!first || k != 0) ? 1u : 0u);
         umma_commit(&pv_done[i]);
       };
       int U = 0, N = 0, it = 0;   // global step, key-set and item counters: barrier phases keep running
@@ -229,24 +236,45 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
     float m_ref = 0.f;
     uint64_t lsum2 = pack_f32x2(0.f, 0.f), lsum2b = pack_f32x2(0.f, 0.f);  // two independent row-sum chains
 
-    int U = 0, N = 0;
-    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+    // One thread per tile feeds the tile's staging buffers by TMA: Q of item w into the P buffers, and (accumulate mode) the
+    // rows the result is added to into the output staging tile, so that every epilogue reads `old` from shared memory.
+    auto load_item = [&](int w) {
+      const int pt = w % p.n_pairs, head = (w / p.n_pairs) % p.heads, b = w / (p.n_pairs * p.heads);
+      const int t0 = pt * 2 * BQ + i * BQ;
+      if (p.accumulate) {
+        mbar_arrive_expect_tx(&res_full[i], OUT_BYTES);
+        tma_load_4d(out_tile, &tmap_o, &res_full[i], 0, t0, head, b);
+        tma_load_4d(out_tile + OUT_PANEL, &tmap_o, &res_full[i], 64, t0, head, b);
+      }
+      mbar_arrive_expect_tx(&q_full[i], 2 * P_BYTES);
+      tma_load_4d(sP + i * 2 * P_BYTES, &tmap_q, &q_full[i], 0, t0, head, b);
+      tma_load_4d(sP + i * 2 * P_BYTES + P_BYTES, &tmap_q, &q_full[i], 64, t0, head, b);
+    };
+    if (store_thread && (int)blockIdx.x < p.n_items) load_item(blockIdx.x);
+
+    int U = 0, N = 0, it = 0;
+    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++it) {
       const int pt = w % p.n_pairs, head = (w / p.n_pairs) % p.heads, b = w / (p.n_pairs * p.heads);
       const int q0 = pt * 2 * BQ;
       const int g0 = (p.tok_offset + q0) / p.rows_per_group;
       const int row = q0 + i * BQ + r;
       const bool row_ok = row < p.q_len;
 
-      // ---- Q row -> TMEM (A operand layout: lane = row, column c holds elements 2c, 2c+1). The previous item's last
-      // score MMA has completed (this thread waited for its s_full), so the columns are free.
+      // ---- Q row -> TMEM (A operand layout: lane = row, column c holds elements 2c, 2c+1). The tile arrived by TMA in
+      // this Q tile's two (idle) P buffers — issued at the end of the previous item, see below — as two SWIZZLE_128B panels;
+      // every thread reads only its own row, as it later writes only its own P row. (Round 1/2 loaded the row with sixteen
+      // 16-byte global loads per thread: 32 different lines per warp instruction, ~3 us of L1 wavefronts per item, and the
+      // same again for the residual row in the first epilogue.) The previous item's last score MMA has completed (this
+      // thread waited for its s_full), so the TMEM columns are free.
       {
-        const uint4* qp = reinterpret_cast<const uint4*>(p.q + (long long)b * p.q_bs + (long long)(row_ok ? row : 0) * p.q_ls + head * D);
+        mbar_wait(&q_full[i], it & 1, 0x9410 | i);
+        const uint8_t* qrow = sP + i * 2 * P_BYTES + r * 128;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t wq[32];
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
-            uint4 v = row_ok ? __ldg(qp + h * 8 + cc) : make_uint4(0, 0, 0, 0);
+            const uint4 v = *reinterpret_cast<const uint4*>(qrow + h * P_BYTES + ((cc ^ (r & 7)) << 4));
             wq[cc * 4] = v.x; wq[cc * 4 + 1] = v.y; wq[cc * 4 + 2] = v.z; wq[cc * 4 + 3] = v.w;
           }
           tmem_st_x32(tQ + h * 32, wq);
@@ -365,7 +393,6 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
         ++U;
       };
 
-      const __nv_bfloat16* orow_g = p.out + (long long)b * p.o_bs + (long long)(row_ok ? row : 0) * p.o_ls + head * D;
       for (int si = 0; si < p.n_sets; ++si, ++N) {
         const int kv_len = p.kv_len[si];
         lsum2 = pack_f32x2(0.f, 0.f);
@@ -378,12 +405,9 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
           if (kv_len % SUB) step(ns - 1, kv_len, std::integral_constant<int, 1>{});
           else step(ns - 1, kv_len, std::integral_constant<int, 0>{});
         }
-        // ---- epilogue of the set: O / l -> bf16 -> (+=) the staging tile (set 0 of an item: first retire the previous
-        // item's TMA store, which still reads the tile)
-        if (si == 0) {
-          if (store_thread) bulk_wait_read0();
-          named_bar_sync(1 + i, 128);
-        }
+        // ---- epilogue of the set: O / l -> bf16 -> (+=) the staging tile. The tile is free (the previous item's TMA store
+        // was retired before this item's Q load was issued) and, in accumulate mode, already holds the rows to add to.
+        if (si == 0 && p.accumulate) mbar_wait(&res_full[i], it & 1, 0x9510 | i);
         mbar_wait(&o_final[i], N & 1, 0x9500 | i);
         tc_fence_after();
         float l_lo, l_hi;
@@ -408,9 +432,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
 #pragma unroll
             for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(o[v8 * 8 + t]) * inv_l;
             if (si > 0 || p.accumulate) {
-              uint4 old;
-              if (si > 0) old = *dst;
-              else old = row_ok ? __ldg(reinterpret_cast<const uint4*>(orow_g) + chunk) : make_uint4(0, 0, 0, 0);
+              const uint4 old = *dst;
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&old);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
@@ -431,10 +453,16 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
       // ---- the item's output leaves as one TMA store per 64-column panel (rows >= q_len clipped by the tensor map)
       fence_proxy_async_smem();
       named_bar_sync(1 + i, 128);
-      if (store_thread && q0 + i * BQ < p.q_len) {
-        tma_store_4d(&tmap_o, out_tile, 0, q0 + i * BQ, head, b);
-        tma_store_4d(&tmap_o, out_tile + OUT_PANEL, 64, q0 + i * BQ, head, b);
-        bulk_commit();
+      if (store_thread) {
+        if (q0 + i * BQ < p.q_len) {
+          tma_store_4d(&tmap_o, out_tile, 0, q0 + i * BQ, head, b);
+          tma_store_4d(&tmap_o, out_tile + OUT_PANEL, 64, q0 + i * BQ, head, b);
+          bulk_commit();
+        }
+        if (w + (int)gridDim.x < p.n_items) {
+          bulk_wait_read0();            // the staging tile has been read: the next item's residual rows may land in it
+          load_item(w + gridDim.x);     // the P buffers are idle too (every thread of the tile passed the last o_final)
+        }
       }
     }
     if (store_thread) bulk_wait0();
@@ -513,9 +541,16 @@ extern "C" int sa_cross_attn3_d128(const sa_cross_attn_args* a, sa_stream_t stre
     uint32_t box[4] = {64, BQ, 1, 1};
     if ((rc = make_tmap_bf16(&to, a->out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
+  CUtensorMap tq;
+  {
+    uint64_t dims[4] = {(uint64_t)D, (uint64_t)a->q_len, (uint64_t)a->heads, (uint64_t)a->batch};
+    uint64_t strides[3] = {(uint64_t)a->q_ls * 2, (uint64_t)D * 2, (uint64_t)a->q_bs * 2};
+    uint32_t box[4] = {64, BQ, 1, 1};
+    if ((rc = make_tmap_bf16(&tq, a->q, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
   if ((rc = ensure_dyn_smem(cross_attn_kernel, SMEM_BYTES, "cross_attn_kernel"))) return rc;
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-  cross_attn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk[0], tv[0], tk[1], tv[1], tk[2], tv[2], to, p);
+  cross_attn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tk[0], tv[0], tk[1], tv[1], tk[2], tv[2], to, tq, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "cross_attn_kernel launch");
   return SA_OK;
