@@ -238,19 +238,27 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
 
     // One thread per tile feeds the tile's staging buffers by TMA: Q of item w into the P buffers, and (accumulate mode) the
     // rows the result is added to into the output staging tile, so that every epilogue reads `old` from shared memory.
-    auto load_item = [&](int w) {
+    // Non-accumulate mode: the next item's first epilogue may only write the staging tile once this item's store has read it
+    // — the store thread retires the store (bulk_wait_read0) before it next arrives anywhere the other threads wait on.
+    auto load_q = [&](int w) {
       const int pt = w % p.n_pairs, head = (w / p.n_pairs) % p.heads, b = w / (p.n_pairs * p.heads);
       const int t0 = pt * 2 * BQ + i * BQ;
-      if (p.accumulate) {
-        mbar_arrive_expect_tx(&res_full[i], OUT_BYTES);
-        tma_load_4d(out_tile, &tmap_o, &res_full[i], 0, t0, head, b);
-        tma_load_4d(out_tile + OUT_PANEL, &tmap_o, &res_full[i], 64, t0, head, b);
-      }
       mbar_arrive_expect_tx(&q_full[i], 2 * P_BYTES);
       tma_load_4d(sP + i * 2 * P_BYTES, &tmap_q, &q_full[i], 0, t0, head, b);
       tma_load_4d(sP + i * 2 * P_BYTES + P_BYTES, &tmap_q, &q_full[i], 64, t0, head, b);
     };
-    if (store_thread && (int)blockIdx.x < p.n_items) load_item(blockIdx.x);
+    auto load_res = [&](int w) {
+      if (!p.accumulate) return;
+      const int pt = w % p.n_pairs, head = (w / p.n_pairs) % p.heads, b = w / (p.n_pairs * p.heads);
+      const int t0 = pt * 2 * BQ + i * BQ;
+      mbar_arrive_expect_tx(&res_full[i], OUT_BYTES);
+      tma_load_4d(out_tile, &tmap_o, &res_full[i], 0, t0, head, b);
+      tma_load_4d(out_tile + OUT_PANEL, &tmap_o, &res_full[i], 64, t0, head, b);
+    };
+    if (store_thread && (int)blockIdx.x < p.n_items) {
+      load_res(blockIdx.x);
+      load_q(blockIdx.x);
+    }
 
     int U = 0, N = 0, it = 0;
     for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++it) {
@@ -410,6 +418,9 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
         if (si == 0 && p.accumulate) mbar_wait(&res_full[i], it & 1, 0x9510 | i);
         mbar_wait(&o_final[i], N & 1, 0x9500 | i);
         tc_fence_after();
+        // the item's last P V has completed: this tile's P buffers are idle until the next item's first softmax step, so
+        // the next item's Q starts travelling now, under this epilogue and the output store
+        if (si == p.n_sets - 1 && store_thread && w + (int)gridDim.x < p.n_items) load_q(w + gridDim.x);
         float l_lo, l_hi;
         lsum2 = add_f32x2(lsum2, lsum2b);
         unpack_f32x2(lsum2, l_lo, l_hi);
@@ -461,7 +472,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
         }
         if (w + (int)gridDim.x < p.n_items) {
           bulk_wait_read0();            // the staging tile has been read: the next item's residual rows may land in it
-          load_item(w + gridDim.x);     // the P buffers are idle too (every thread of the tile passed the last o_final)
+          load_res(w + gridDim.x);
         }
       }
     }
