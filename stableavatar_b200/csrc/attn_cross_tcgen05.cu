@@ -374,7 +374,11 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tk0, const __grid_constant
         float pe[64];
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
-          SA_EXP2_PAIR(t, x2[t], pe[2 * t], pe[2 * t + 1]);   // the self-attention kernel's mix of MUFU and FMA-pipe exp2
+          // the self-attention kernel's mix of MUFU and FMA-pipe exp2 — except in the windowed step: where a row's window
+          // sits inside the 64-key step depends on the item's first window, i.e. on how the tokens are sharded, and the
+          // sequence-parallel forward must stay bit-identical to the single-GPU one
+          if constexpr (MASK == 2) exp2_pair<false>(x2[t], pe[2 * t], pe[2 * t + 1]);
+          else SA_EXP2_PAIR(t, x2[t], pe[2 * t], pe[2 * t + 1]);
         }
         uint64_t la = lsum2, lb = lsum2b, lc = pack_f32x2(0.f, 0.f), ld = pack_f32x2(0.f, 0.f);
 #pragma unroll
