@@ -156,3 +156,37 @@ def test_14b_state_dict_keys_match_reference_names():
     got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     assert got == {k: tuple(v) for k, v in want.items()}
     assert "vocal_projector.proj_model.proj_2.weight" in got and "vocal_projector.proj_model.proj.weight" not in got
+
+
+def test_round2_entry_points_reject_bad_arguments_without_a_gpu(lib):
+    """Halo-staged conv and the attention with the fused sequence-parallel O store validate before any CUDA call."""
+    from stableavatar_b200 import ops
+    sup = lib.sa_conv3d_halo_supported
+    assert sup(96, 96, 3, 3, 3, 1, 0) and sup(192, 192, 3, 3, 3, 1, 1) and sup(192, 384, 3, 3, 3, 1, 0) and sup(384, 192, 1, 3, 3, 1, 0)
+    assert sup(96, 3, 3, 3, 3, 1, 2)                                          # the video head
+    assert not sup(96, 96, 3, 1, 1, 1, 0) and not sup(32, 96, 3, 3, 3, 1, 0) and not sup(96, 96, 3, 3, 3, 2, 0)
+    assert not sup(96, 128, 3, 3, 3, 1, 0) and not sup(96, 96, 3, 3, 3, 1, 3)
+    a = ops.ConvArgs(inp=16, w=16, bias=16, out=16, Tout=1, H=8, W=8, Cin=32, Cout=96, KT=3, KH=3, KW=3, out_mode=0,
+                     pad_h=-1, pad_w=-1, stride_t=1)
+    assert lib.sa_conv3d_halo_cl(C.byref(a), None) == -3 and b"Cout 96" in lib.sa_last_error()
+    assert lib.sa_conv3d_halo_cl(None, None) == -1
+    from stableavatar_b200 import _lib as L
+    at = L.AttnArgs()
+    assert lib.sa_flash_attn_d128_sp(C.byref(at), None, 1, 1, C.c_int64(0), C.c_int64(0), None) == -1            # no destinations
+    assert b"destination" in lib.sa_last_error()
+
+
+def test_halo_conv_weight_packing_layout():
+    """ops.pack_conv_weight_halo: [Cout, KT, KH, KW, Cin] -> [Cout / BN][taps][Cin / 8][BN][8], zero rows up to 16 for the head."""
+    from stableavatar_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for cout, cin, kt in ((96, 48, 3), (384, 96, 1), (3, 96, 3)):
+        w5 = torch.randn(cout, kt, 3, 3, cin, generator=g)
+        p = ops.pack_conv_weight_halo(w5)
+        bn = 16 if cout <= 16 else (96 if cout == 96 else 192)
+        assert p.dtype == torch.bfloat16 and p.shape == (max(cout, bn) // bn, kt * 9, cin // 8, bn, 8)
+        for (n, t, c) in ((0, 0, 0), (cout - 1, kt * 9 - 1, cin - 1), (cout // 2, 4, 17 % cin)):
+            want = w5[n, t // 9, (t % 9) // 3, t % 3, c].to(torch.bfloat16)
+            assert p[n // bn, t, c // 8, n % bn, c % 8] == want
+        if cout < 16:
+            assert (p[0, :, :, cout:] == 0).all()
