@@ -30,7 +30,7 @@ constexpr int TW = 8, TH = 16, BM = TW * TH;
 constexpr int HW_ = TW + 2, HH_ = TH + 2, HPOS = HW_ * HH_;   // 10 x 18 halo positions
 constexpr int PLANE = HPOS * 16 + 16;                          // + 16: consecutive planes start in different banks
 constexpr int HALO_BUFS = 2;
-constexpr int MAX_W_STAGES = 6;
+constexpr int MAX_W_STAGES = 9;               // 9 = the taps of one halo stage: lets the last stage of a pass keep all of them resident
 constexpr int NUM_THREADS = 320;
 constexpr int PRODUCERS = 128;
 constexpr int TMEM_COLS = 512;
@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Param
   uint64_t* hempty = hfull + HALO_BUFS;
   uint64_t* wfull = hempty + HALO_BUFS;
   uint64_t* wempty = wfull + MAX_W_STAGES;
-  uint64_t* tfull = wempty + MAX_W_STAGES;
-  uint64_t* tempty = tfull + 1;                    // [G]
+  uint64_t* tfull = wempty + MAX_W_STAGES;         // [G]  accumulator g of the pass is complete
+  uint64_t* tempty = tfull + 4;                    // [G]  the epilogue has accumulator g in registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -107,8 +107,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Param
         mbar_init(&wfull[s], 1);
         mbar_init(&wempty[s], 1);
       }
-      mbar_init(tfull, 1);
-      for (int g = 0; g < G; ++g) mbar_init(&tempty[g], 4);
+      for (int g = 0; g < G; ++g) {
+        mbar_init(&tfull[g], 1);
+        mbar_init(&tempty[g], 4);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -153,35 +155,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Param
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
       uint32_t wit = 0, hit = 0, pcount = 0;
+      // With 9 weight stages in the ring (BN 96 / 16) stage index == tap, and the LAST halo stage of a pass runs tile by
+      // tile instead of tap by tap (all nine taps resident): tile g is complete 9 x CGK/16 MMAs after tile g - 1, so the
+      // epilogue drains accumulator g while g + 1 ... are still being computed and the next pass finds its accumulators
+      // free — the issuer sat 27 % of its time on tempty when all G tiles finished together (profiles/r02_conv_halo_ncu.txt).
+      const bool seq_last = p.w_stages == 9;
+      auto mma_tile_tap = [&](uint32_t h_addr, uint32_t w_addr, int g, int tap, int hs) {
+        const uint32_t tap_off = ((tap / 3) * HW_ + (tap % 3)) * 16;
+#pragma unroll
+        for (int j = 0; j < CGK / 16; ++j) {
+          const uint64_t adesc = umma_smem_desc(h_addr + g * HALO_TILE + 2 * j * PLANE + tap_off, PLANE, HW_ * 16, 0);
+          const uint64_t bdesc = umma_smem_desc(w_addr + 2 * j * (BN * 16), BN * 16, 128, 0);
+          umma_ss(tmem_base + g * BN, adesc, bdesc, idesc, (hs | tap | j) != 0);
+        }
+      };
       for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x, ++pcount) {
         for (int hs = 0; hs < stages_per_pass; ++hs, ++hit) {
           const int hb = hit & 1;
           mbar_wait(&hfull[hb], (hit >> 1) & 1, 0xb200 | hb);
           const uint32_t h_addr = smem_u32(s_halo + hb * HALO_STAGE);
-          for (int tap = 0; tap < 9; ++tap, ++wit) {
-            const int s = wit % p.w_stages;
-            mbar_wait(&wfull[s], (wit / p.w_stages) & 1, 0xb300 | s);
-            tc_fence_after();
-            const uint32_t w_addr = smem_u32(s_w + s * p.w_stage_bytes);
-            const uint32_t tap_off = ((tap / 3) * HW_ + (tap % 3)) * 16;
-#pragma unroll
+          if (seq_last && hs == stages_per_pass - 1) {
             for (int g = 0; g < G; ++g) {
-              if (hs == 0 && tap == 0) {   // first MMA of the pass on accumulator g: the epilogue must have drained it
+              if (hs == 0) {               // single-stage pass: this is also the first MMA on accumulator g
                 mbar_wait(&tempty[g], (pcount & 1) ^ 1, 0xb400 | g);
                 tc_fence_after();
               }
-#pragma unroll
-              for (int j = 0; j < CGK / 16; ++j) {
-                const uint64_t adesc = umma_smem_desc(h_addr + g * HALO_TILE + 2 * j * PLANE + tap_off, PLANE, HW_ * 16, 0);
-                const uint64_t bdesc = umma_smem_desc(w_addr + 2 * j * (BN * 16), BN * 16, 128, 0);
-                umma_ss(tmem_base + g * BN, adesc, bdesc, idesc, (hs | tap | j) != 0);
+              for (int tap = 0; tap < 9; ++tap) {
+                if (g == 0) {
+                  mbar_wait(&wfull[tap], ((wit + tap) / 9) & 1, 0xb300 | tap);
+                  tc_fence_after();
+                }
+                mma_tile_tap(h_addr, smem_u32(s_w + tap * p.w_stage_bytes), g, tap, hs);
               }
+              umma_commit(&tfull[g]);
             }
-            umma_commit(&wempty[s]);
+            for (int tap = 0; tap < 9; ++tap) umma_commit(&wempty[tap]);
+            wit += 9;
+          } else {
+            for (int tap = 0; tap < 9; ++tap, ++wit) {
+              const int s = wit % p.w_stages;
+              mbar_wait(&wfull[s], (wit / p.w_stages) & 1, 0xb300 | s);
+              tc_fence_after();
+              const uint32_t w_addr = smem_u32(s_w + s * p.w_stage_bytes);
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                if (hs == 0 && tap == 0) {   // first MMA of the pass on accumulator g: the epilogue must have drained it
+                  mbar_wait(&tempty[g], (pcount & 1) ^ 1, 0xb400 | g);
+                  tc_fence_after();
+                }
+                mma_tile_tap(h_addr, w_addr, g, tap, hs);
+              }
+              umma_commit(&wempty[s]);
+            }
+            if (hs == stages_per_pass - 1)
+              for (int g = 0; g < G; ++g) umma_commit(&tfull[g]);
           }
           umma_commit(&hempty[hb]);
         }
-        umma_commit(tfull);
       }
     }
   } else if (warp < 6) {
@@ -195,12 +225,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_halo_kernel(const Param
     named_bar_sync(1, 128);
     uint32_t pcount = 0;
     for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x, ++pcount) {
-      mbar_wait(tfull, pcount & 1, 0xb500);
-      tc_fence_after();
       const int r = q * 32 + lane;
       const int nt = pass / p.passes_per_nt, grp = pass % p.passes_per_nt;
 #pragma unroll 1
       for (int g = 0; g < G; ++g) {
+        mbar_wait(&tfull[g], pcount & 1, 0xb500 | g);
+        tc_fence_after();
         const int tile = grp * G + g;
         int t = 0, h0 = 0, w0 = 0;
         const bool tile_ok = tile < p.num_tiles;
