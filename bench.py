@@ -26,7 +26,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "s/denoise-step 1.3B @480x832x81f"
-SELF_ATTN_DRAM_BYTES_B3 = 918.55e6 + 288.42e6   # ncu --set full of one flash_attn_v8_kernel launch inside bench.py (profiles/r01_selfattn_in_bench_ncu.txt)
+SELF_ATTN_DRAM_BYTES_B3 = 913.93e6 + 286.01e6   # ncu --set full of one flash_attn_v8_kernel launch inside bench.py (profiles/r02_selfattn_in_bench_ncu.txt)
 UNIT = "s/step"
 
 
@@ -462,7 +462,7 @@ def run_b200(args):
             "roofline": {"kernel": "attn8::flash_attn_v8_kernel (self-attention, sa_flash_attn_d128)", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"] if achieved else None,
                          "traffic": SELF_ATTN_DRAM_BYTES_B3 if (world == 1 and (args.frames, args.height, args.width) == (81, 480, 832)) else None,
-                         "traffic_source": "profiles/r01_selfattn_in_bench_ncu.txt (ncu --set full, dram__bytes_read+write of one "
+                         "traffic_source": "profiles/r02_selfattn_in_bench_ncu.txt (ncu --set full, dram__bytes_read+write of one "
                                            "B=3 self-attention launch; algorithmic q+k+v+o = 1208 MB); null at N > 1 (ncu is single-GPU only "
                                            "and the 4x2 split at N = 8 reads each K/V chunk on two ranks)",
                          "peak_source": f"{peaks['src']} sustained bf16 (MEASURED_PEAKS.json)",
