@@ -16,7 +16,7 @@
 //     shared memory before its Q is;
 //   * the per-set results are summed in a shared-memory staging tile (bf16, every partial result rounded to bf16 before
 //     the bf16 add, set order text, image, audio — the arithmetic of three separate launches; bit for bit for the plain
-//     sets, while the windowed set may pick a different one-in-eight of its keys for the FMA-pipe exponential) and leave the
+//     sets; the windowed step keeps all its exponentials on MUFU, see the step body) and leave the
 //     SM once per item as a TMA store (rows beyond q_len are clipped by the tensor map).
 //
 // The audio set is one 64-key step: the keys of the (at most 64 / A) consecutive windows that the item's 256 rows can

@@ -312,9 +312,9 @@ flash_attn_v8_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_co
         // exactly at the XU rate (8 cycles per warp instruction); the two softmax warps of an SM sub-partition share that
         // pipe, so a step costs each of them >= 1024 cycles of MUFU time — as much as the step's MMAs take on the tensor
         // pipe — plus ~400 cycles of barrier waits, TMEM load, row max and fences (in-kernel event trace,
-        // profiles/r02_attn_investigation.md). One eighth of the exponentials therefore take the FMA / ALU pipes (exp2_pair):
-        // +3.5 % in a 30-round randomised rotation at B = 3 (r02_attn_ab_emulation_30rounds.log), while a quarter or more
-        // loses 1-2 % again (the extra ~10 instructions per pair cost issue slots and power). Round-2 variants that attacked
+        // profiles/r02_attn_investigation.md). Three sixteenths of the exponentials therefore take the FMA / ALU pipes
+        // (exp2_pair): +3.5 ... +5 % in 30-round randomised rotations at B = 3 (r02_attn_ab_emulation_30rounds*.log), while
+        // a quarter or more loses it again (the extra ~10 instructions per pair cost issue slots and power). Round-2 variants that attacked
         // the rest and did NOT pay, measured the same way: TMEM load + row max of S(u+1) hidden under
         // the exponentials of step u (224 registers through setmaxnreg): -8 ... -17 %; a shared 128-column score buffer
         // with 128-key steps handed between the two Q tiles: +-2 %. Sources: profiles/experiments/.

@@ -273,7 +273,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 // degree-3 minimax polynomial of 2^f on [-0.5, 0.5] — max relative error 7.5e-5, far inside the bf16 rounding of P — and
 // the integer part added into the exponent field). x <= the lazy-rescale threshold (8) by construction; the clamp keeps the exponent
 // add from wrapping for scores far below the running max.
-constexpr int kEmuPairsPer16 = 2;   // of every 16 packed pairs of exponentials, this many (evenly spread) skip the XU pipe
+constexpr int kEmuPairsPer16 = 3;   // of every 16 packed pairs of exponentials, this many (evenly spread) skip the XU pipe
 template <bool EMULATE>
 __device__ __forceinline__ void exp2_pair(uint64_t x2, float& p0, float& p1) {
   float x0, x1;

@@ -204,8 +204,9 @@ def _cross_inputs(B, Lq, Hh, G, A, seed):
 def test_fused_cross_attention_equals_three_launches(ops, Lq, G, tok_offset, L_total):
     """sa_cross_attn3_d128 (text + image + windowed audio in one launch) against three sa_flash_attn_d128 launches with
     accumulate and against fp32 torch SDPA per set. The plain sets are bit-identical by construction (next test); the
-    windowed set sits at a different column offset of its 64-key step than a separate 15-key launch, so a different
-    one-in-eight of its keys takes the FMA-pipe exponential (relative error 7.5e-5 before the bf16 rounding of P)."""
+    windowed step of the fused kernel keeps every exponential on MUFU (where a window sits inside the step depends on the
+    token sharding, and the sequence-parallel forward must stay bit-identical), while a separate 15-key launch takes a few
+    of them from the FMA-pipe polynomial (relative error 7.5e-5 before the bf16 rounding of P)."""
     B, Hh, A = 2, 3, 15
     gs = L_total // G
     q, (kt, vt), (ki, vi), (ka, va) = _cross_inputs(B, Lq, Hh, G, A, 11)
