@@ -66,6 +66,24 @@ def test_ragged_spatial_tiles_vs_oracle(vae):
     assert rel(out, ref) < 2e-2 and psnr(out, ref) > 35
 
 
+def test_opt_in_graph_replay_of_steady_state_chunks_is_bit_identical(vae):
+    """use_cuda_graph: chunk 2 of the second decode of a shape is captured and replayed for chunks 2.. (and for every later
+    decode of that shape); the frames must not change, also not for another latent decoded through the cached graph."""
+    z1 = synth.det_normal("vae_zg1", (1, 16, 6, 12, 16)).cuda()
+    z2 = synth.det_normal("vae_zg2", (1, 16, 6, 12, 16)).cuda()
+    want1, want2 = vae.decode(z1).sample.clone(), vae.decode(z2).sample.clone()
+    vae.use_cuda_graph = True
+    try:
+        vae.decode(z1)                                   # shape seen once: eager
+        got1 = vae.decode(z1).sample.clone()             # captures at chunk 2, replays the rest
+        assert vae._dec_graph is not None
+        got2 = vae.decode(z2).sample.clone()             # replays the cached graph on another latent
+    finally:
+        vae.use_cuda_graph = False
+        vae._dec_graph = vae._dec_seen = None
+    assert torch.equal(got1, want1) and torch.equal(got2, want2)
+
+
 def test_decode_is_idempotent_across_calls(vae):
     """The ring-buffer caches are reset per decode: the same latent decodes to the same frames twice."""
     z = synth.det_normal("vae_z", (1, 16, 3, 6, 8)).cuda()
