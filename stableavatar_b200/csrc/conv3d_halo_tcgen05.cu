@@ -1,24 +1,30 @@
-// conv3d_halo_tcgen05.cu — the 3x3x3 'same' causal convolutions of the Wan VAE at 96 / 192 output channels (70 % of the
-// decoder's FLOPs: every conv of the two highest-resolution stages) as an implicit GEMM whose input tile is staged ONCE.
+// conv3d_halo_tcgen05.cu — the (1|3)x3x3 'same' stride-1 convolutions of the Wan VAE with 96 / 192 / 384 output channels and
+// the 96 -> 3 video head (95 % of the decoder's FLOPs: every ResidualBlock conv, the 2-D convs of the upsamplers, the head)
+// as an implicit GEMM whose input tile is staged ONCE.
 //
 // conv3d_tcgen05.cu re-loads the [128 positions x Cin] tile for each of the 27 taps and the tap's weights for every tile:
 // 147 bytes per SM-clock of L2 -> shared-memory traffic at full tensor rate, three times what the L2 delivers — it runs at
-// 29 % (Cout 96) / 52 % (Cout 192) of the tensor pipe. Here, per time tap kt and channel group:
+// 0.44 (Cout 96) / 0.70 (Cout 192) of the sustained tensor rate. Here, per time tap kt and channel group:
 //
 //   * the (16+2) x (8+2) halo of a 16 h x 8 w output tile is copied to shared memory once (cp.async, 16-byte chunks, zero
 //     fill outside the frame = the 'same' padding) in the tcgen05 NO-SWIZZLE K-major layout: plane c = channels 8c..8c+7,
 //     inside a plane position (hh, ww) at (hh * 10 + ww) * 16 bytes. The A operand of spatial tap (kh, kw) is then the
 //     SAME buffer at a start offset of (kh * 10 + kw) * 16 bytes with SBO = 160 bytes (one halo row: the next 8 output
 //     positions) and LBO = plane size — 9 taps, no copy, no im2col;
-//   * a weight stage (one tap x channel group, pre-packed [tap][Cin/8][Cout][8] on the host = the same layout with SBO 128,
-//     LBO Cout * 16) arrives as one cp.async.bulk and is used by G output tiles whose accumulators sit side by side in TMEM
-//     (G = 4 x 96 or 2 x 192 columns), so weights cross L2 -> SM once per G tiles: 64 / G bytes per SM-clock.
+//   * a weight stage (one tap x channel group, pre-packed [Cout/BN][tap][Cin/8][BN][8] on the host = the same layout with
+//     SBO 128, LBO BN * 16) arrives as one cp.async.bulk and is used by G output tiles whose accumulators sit side by side
+//     in TMEM (G = 4 x 96 or 2 x 192 columns; Cout 384 = two passes over 192-channel tiles), so weights cross L2 -> SM
+//     once per G tiles: 64 / G bytes per SM-clock;
+//   * the epilogue pulls an accumulator into registers and hands it back before bias / residual / stores; with nine weight
+//     stages resident (BN 96 / 16) the last halo stage of a pass is issued tile by tile, one completion barrier per tile.
 //
-// L2 -> SM traffic at full tensor rate: 29 (Cout 96) / 39 (Cout 192) bytes per SM-clock instead of 147 / 120.
+// L2 -> SM traffic at full tensor rate: 29 (Cout 96) / 39 (Cout 192) bytes per SM-clock instead of 147 / 120. Measured
+// (tools/conv_bench.py): 96 -> 96 @4x480x832 608 -> 1070 TFLOP/s, 192 -> 192 @4x240x416 980 -> 1381.
 // Warps: 0 = weight producer, 1 = MMA issuer, 2-5 = epilogue (TMEM lane quarter = warp % 4), 6-9 = halo producers.
 //
-// Replaces CausalConv3d inside ResidualBlock of wan/models/wan_vae.py (:20-39, 189-223) for those shapes; everything else
-// (other channel counts, 2-D / strided convs, the head) stays on conv3d_tcgen05.cu.
+// Replaces CausalConv3d / Conv2d of wan/models/wan_vae.py (:20-39, 69-143, 189-223, 438-441) for those shapes; everything
+// else (3- / 16- / 32-channel inputs, (3,1,1) time convs, strided encoder convs, fp32 encoder head, frames too small to fill
+// the coarse work units) stays on conv3d_tcgen05.cu.
 #include "../../include/stableavatar_b200.h"
 #include "sa_host.h"
 #include "sa_ptx.cuh"
