@@ -73,9 +73,11 @@ __global__ void __launch_bounds__(THREADS) attn_small_kernel(const Params p) {
 #pragma unroll
         for (int i = 0; i < MAXQ; ++i) {
           if (i < p.q_len) {
-            const float* qr = sq + i * p.d + c * 8;
-#pragma unroll
-            for (int t = 0; t < 8; ++t) sc[i] = fmaf(qr[t], kv[t], sc[i]);
+            // two 16-byte broadcast reads (d % 8 == 0 keeps every chunk 32-byte aligned) instead of eight scalar ones
+            const float4 qa = *reinterpret_cast<const float4*>(sq + i * p.d + c * 8);
+            const float4 qb4 = *reinterpret_cast<const float4*>(sq + i * p.d + c * 8 + 4);
+            sc[i] = fmaf(qa.x, kv[0], fmaf(qa.y, kv[1], fmaf(qa.z, kv[2], fmaf(qa.w, kv[3], sc[i]))));
+            sc[i] = fmaf(qb4.x, kv[4], fmaf(qb4.y, kv[5], fmaf(qb4.z, kv[6], fmaf(qb4.w, kv[7], sc[i]))));
           }
         }
       }
